@@ -1,0 +1,243 @@
+/*
+ * pairnet_b200 -- C-ABI of the B200 (sm_100a) implementation of Pair-Net's relation-head hot path.
+ *
+ * The reference (king159/Pair-Net) is 100 % Python and has NO FFI of its own: every entry point
+ * below replaces a span of eager PyTorch calls in
+ *     pairnet/models/relation_heads/pairnet_head.py   (class CrossHead2)
+ *     pairnet/models/frameworks/cnn_factory.py        (class ConvTiny)
+ * and is bound from Python with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer valid on `stream` (a cudaStream_t passed as void*).
+ *   - caller owns all buffers; nothing is allocated behind the caller's back; scratch memory is
+ *     passed in as (ws, ws_bytes) and sized with the matching *_workspace_bytes() query.
+ *   - return value: 0 = ok; <0 = PN_ERR_* ; >0 = a cudaError_t raised by a launch.
+ *     pn_last_error_string() describes the last failure on the calling thread.  Never throws.
+ *   - all activations are fp32, row-major, BATCH-MAJOR ([B, seq, d]); the reference's internal
+ *     [seq, B, d] layout is only a view choice (outputs of CrossHead2.forward are batch-first).
+ *   - asynchronous: kernels are enqueued on `stream`; CUDA-graph capturable (no sync, no malloc).
+ */
+#ifndef PAIRNET_B200_H_
+#define PAIRNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_VERSION 100          /* 0.1.0 */
+#define PN_MAX_LAYERS 16
+#define PN_MAX_LEVELS 4
+#define PN_EMBED_DIMS 256       /* compiled-in embed dim (all shipped Pair-Net configs use 256) */
+#define PN_HEAD_DIM 32          /* 256 / 8 heads */
+
+#define PN_ERR_BAD_ARG      (-1)
+#define PN_ERR_UNSUPPORTED  (-2)
+#define PN_ERR_WORKSPACE    (-3)
+
+#if defined(__GNUC__)
+#define PN_API __attribute__((visibility("default")))
+#else
+#define PN_API
+#endif
+
+typedef void* pn_stream_t;
+
+/* nn.Linear: y = x W^T + b ; w is [out, in] row-major (torch layout), b may be NULL */
+typedef struct { const float* w; const float* b; } PnLinear;
+/* nn.LayerNorm(256), eps 1e-5 */
+typedef struct { const float* gamma; const float* beta; } PnNorm;
+/* nn.MultiheadAttention(256, 8): in_proj_weight [768,256] = [Wq;Wk;Wv], in_proj_bias [768] */
+typedef struct {
+  const float* in_proj_w; const float* in_proj_b;
+  const float* out_proj_w; const float* out_proj_b;
+} PnMHA;
+/* mmcv BaseTransformerLayer, operation_order (cross_attn, norm, self_attn, norm, ffn, norm)
+ * -- configs/mask2former/pairnet.py:72-139 */
+typedef struct {
+  PnMHA cross_attn;      /* attentions.0 */
+  PnMHA self_attn;       /* attentions.1 */
+  PnLinear ffn1;         /* ffns.0.layers.0.0  [ffn, 256] */
+  PnLinear ffn2;         /* ffns.0.layers.1    [256, ffn] */
+  PnNorm norm[3];        /* norms.0..2 */
+} PnDecoderLayer;
+/* Linear-ReLU-Linear-ReLU-Linear (mask_embed, sub_query_update, obj_query_update) */
+typedef struct { PnLinear l[3]; } PnMlp3;
+/* ConvTiny: conv_layers.{0,1,2}.0  w0 [mid,1,7,7]  w1 [mid,mid,7,7]  w2 [1,mid,7,7] */
+typedef struct { const float* w[3]; const float* b[3]; int mid_channels; } PnConvTiny;
+
+/* ------------------------------------------------------------------ library */
+PN_API int pn_version(void);
+PN_API const char* pn_last_error_string(void);
+/* fills SM count and compute capability of the current device */
+PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ row 1: level prep
+ * replaces pairnet_head.py:268-288 (flatten/permute + level_embed, SinePositionalEncoding). */
+/* pos [h*w, 256] token-major sine encoding of an all-false mask (input independent). */
+PN_API int pn_sine_posenc(float* pos, int h, int w, pn_stream_t stream);
+/* mem [B,256,hw] -> x [B,hw,256] = mem^T + level_embed ; xp = x + pos */
+PN_API int pn_level_prep(const float* mem, const float* level_embed, const float* pos,
+                  float* x, float* xp, int B, int hw, pn_stream_t stream);
+
+/* ------------------------------------------------------------------ row 2: forward_head
+ * replaces pairnet_head.py:216-258 (post_norm, cls_embed, mask_embed, einsum, bilinear, threshold) */
+/* bilinear (align_corners=False) resize of mask_features [B,256,H,W] to [B,256,ldo] rows of
+ * h*w valid pixels (ldo >= h*w, multiple of 32, zero padded).  Linear, so it commutes with the
+ * einsum over channels: sign(E . resize(F)) == sign(resize(E . F)) up to fp32 rounding. */
+PN_API int pn_mask_feature_resize(const float* mask_feature, float* out, int B, int H, int W,
+                           int h, int w, int ldo, pn_stream_t stream);
+/* attention-mask bits: bit p of word [b][q][p/32] = 1 (blocked) iff sum_c E[b,q,c] F[b,c,p] < 0.
+ * rowany[b*N+q] is OR-ed with 1 when the row has at least one unblocked key (must be zeroed by
+ * the caller).  E [B,N,256], F [B,256,ldf], bits [B,N,words] with words = ldf/32. */
+PN_API int pn_attn_mask_bits(const float* E, const float* F, uint32_t* bits, int* rowany,
+                      int B, int N, int hw, int ldf, pn_stream_t stream);
+/* mask_pred [B,N,HW] = E [B,N,256] . F [B,256,HW]   (the einsum "bqc,bchw->bqhw") */
+PN_API int pn_mask_pred(const float* E, const float* F, float* mask_pred, int B, int N, int HW,
+                 pn_stream_t stream);
+
+/* ------------------------------------------------------------------ generic bricks */
+/* y[M,N] = act(x[M,K] W[N,K]^T + b) (+ resid[M,N]);  relu: 0/1 */
+PN_API int pn_linear(const float* x, int ldx, const float* w, const float* b, const float* resid,
+              float* y, int ldy, int M, int N, int K, int relu, pn_stream_t stream);
+/* y = LayerNorm(x + resid) over 256 channels (resid may be NULL) */
+PN_API int pn_add_layernorm(const float* x, const float* resid, const float* gamma, const float* beta,
+                     float* y, int M, pn_stream_t stream);
+/* scaled-dot-product attention core of nn.MultiheadAttention for already projected q/k/v.
+ * q [B,Nq,*] (row stride ldq), k,v [B,Nk,*]; 8 heads x 32; mask_bits (nullable) [B,Nq,words],
+ * rowany (nullable) [B*Nq]: rows whose flag is 0 ignore the mask (pairnet_head.py:300).
+ * out [B,Nq,256]. ws >= pn_mha_workspace_bytes(B,Nq,Nk). */
+PN_API size_t pn_mha_workspace_bytes(int B, int Nq, int Nk);
+PN_API int pn_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                const uint32_t* mask_bits, int mask_words, const int* rowany,
+                float* out, int B, int Nq, int Nk, void* ws, size_t ws_bytes, pn_stream_t stream);
+
+/* ------------------------------------------------------------------ rows 3 (+1,2): M2F decoder
+ * replaces pairnet_head.py:262-320 minus the pixel decoder call. */
+typedef struct {
+  int num_queries;            /* N  (num_obj_query) */
+  int num_layers;             /* 9 */
+  int num_levels;             /* 3 */
+  int ffn_dims;               /* 2048 */
+  int num_cls;                /* num_classes + 1 = 134 */
+  const float* query_feat;    /* query_feat.weight  [N,256] */
+  const float* query_embed;   /* query_embed.weight [N,256] */
+  const float* level_embed;   /* level_embed.weight [levels,256] */
+  PnNorm post_norm;           /* transformer_decoder.post_norm */
+  PnLinear cls_embed;         /* [num_cls,256] */
+  PnMlp3 mask_embed;
+  PnDecoderLayer layers[PN_MAX_LAYERS];
+} PnM2FWeights;
+
+typedef struct {
+  int B;
+  int H4, W4;                          /* mask_features spatial size */
+  const float* mask_features;          /* [B,256,H4,W4] */
+  int h[PN_MAX_LEVELS], w[PN_MAX_LEVELS];
+  const float* memory[PN_MAX_LEVELS];  /* multi_scale_memorys[l] [B,256,h,w], low -> high res */
+  const float* pos[PN_MAX_LEVELS];     /* optional precomputed pn_sine_posenc tables (NULL = compute) */
+} PnM2FInputs;
+
+typedef struct {
+  float* query_out;     /* [B,N,256]   last layer query_feat (pre post_norm) -- PPN input */
+  float* cls_pred;      /* [B,N,num_cls] */
+  float* mask_pred;     /* [B,N,H4*W4] */
+  float* query_trace;   /* optional [layers,B,N,256] per-layer query_feat (NULL = skip) */
+  uint32_t* mask_trace; /* optional [layers,B,N,trace_words] attention-mask bits (NULL = skip) */
+  int trace_words;
+} PnM2FOutputs;
+
+PN_API size_t pn_m2f_decoder_workspace_bytes(const PnM2FWeights* w, const PnM2FInputs* in);
+PN_API int pn_m2f_decoder_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2FOutputs* out,
+                           void* ws, size_t ws_bytes, pn_stream_t stream);
+
+/* ------------------------------------------------------------------ rows 4-8: Pair Proposal Network
+ * replaces pairnet_head.py:322-351,365 and cnn_factory.py:49-53.
+ * query [B,N,256] -> sub/obj MLP -> L2 normalise -> importance_raw = S O^T -> ConvTiny ->
+ * top-k (k=K, descending, ties: lower flat index first) -> sub_pos = idx / N, obj_pos = idx % N ->
+ * pair_feat [B,2K,256] = [query[sub_pos] ; query[obj_pos]].
+ * conv == NULL selects the "pair matrix + top-k only" microbenchmark mode (BASELINE config 5a).
+ * sub_mlp == NULL: `query` is taken as already-normalised sub embeddings and `query_obj` as obj
+ * embeddings (microbenchmark inputs); otherwise query_obj must be NULL. */
+PN_API size_t pn_ppn_workspace_bytes(int B, int N, int K, int mid_channels);
+PN_API int pn_ppn_forward(const float* query, const float* query_obj, const PnMlp3* sub_mlp,
+                   const PnMlp3* obj_mlp, const PnConvTiny* conv,
+                   float* importance_raw /* [B,N,N] nullable */, float* importance /* [B,N,N] */,
+                   int64_t* topk_idx /* [B,K] nullable */, int64_t* sub_pos /* [B,K] */,
+                   int64_t* obj_pos /* [B,K] */, float* pair_feat /* [B,2K,256] nullable */,
+                   int B, int N, int K, void* ws, size_t ws_bytes, pn_stream_t stream);
+/* stand-alone pieces (stage-wise parity tests) */
+PN_API int pn_conv_tiny(const float* x /* [B,N,N] */, const PnConvTiny* conv, float* y /* [B,N,N] */,
+                 int B, int N, void* ws, size_t ws_bytes, pn_stream_t stream);
+PN_API int pn_topk_pairs(const float* importance /* [B,N*N] */, int64_t* topk_idx, int64_t* sub_pos,
+                  int64_t* obj_pos, const float* query /* nullable */, float* pair_feat /* nullable */,
+                  int B, int N, int K, pn_stream_t stream);
+
+/* ------------------------------------------------------------------ rows 9-10: Relation Fusion
+ * replaces pairnet_head.py:353-378. */
+typedef struct {
+  int num_rel_queries;           /* R */
+  int num_layers;                /* 6 */
+  int ffn_dims;                  /* 2048 */
+  int num_rel_cls;               /* 56 */
+  const float* rel_query_feat;   /* [R,256] */
+  const float* rel_query_embed;  /* [R,256]  query_pos */
+  const float* rel_query_embed2; /* [2K,256] key_pos   (rel_query_embed3 is dead in the reference) */
+  PnLinear rel_cls_embed;        /* [num_rel_cls,256] */
+  PnDecoderLayer layers[PN_MAX_LAYERS];
+} PnRelWeights;
+
+PN_API size_t pn_relation_fusion_workspace_bytes(int B, int R, int K2, int ffn_dims);
+PN_API int pn_relation_fusion_forward(const PnRelWeights* w, const float* pair_feat /* [B,K2,256] */,
+                               float* rel_preds /* [B,R,num_rel_cls] */,
+                               float* rel_feat_out /* [B,R,256] nullable */,
+                               int B, int K2, void* ws, size_t ws_bytes, pn_stream_t stream);
+
+/* ------------------------------------------------------------------ row 11: output gathers
+ * replaces pairnet_head.py:380-403: dst[b,r,:] = src[b, idx[b,r], :] (row length L floats) */
+PN_API int pn_gather_rows(const float* src, const int64_t* idx, float* dst, int B, int Nsrc, int R,
+                   long long L, pn_stream_t stream);
+
+/* ------------------------------------------------------------------ whole hot path
+ * CrossHead2.forward minus the pixel decoder (pairnet_head.py:264-417) in one call. */
+typedef struct {
+  PnM2FWeights m2f;
+  PnMlp3 sub_query_update, obj_query_update;
+  PnConvTiny update_importance;
+  PnRelWeights rel;
+} PnHeadWeights;
+
+typedef struct {
+  float* cls;          /* [B,N,num_cls] */
+  float* mask;         /* [B,N,H4*W4] */
+  float* importance;   /* [B,N,N] */
+  float* rel;          /* [B,R,num_rel_cls] */
+  int64_t* sub_pos;    /* [B,K] */
+  int64_t* obj_pos;    /* [B,K] */
+  float* sub;          /* [B,K,num_cls]  nullable */
+  float* obj;          /* [B,K,num_cls]  nullable */
+  float* sub_seg;      /* [B,K,H4*W4]    nullable */
+  float* obj_seg;      /* [B,K,H4*W4]    nullable */
+  /* optional taps for stage-wise parity tests (all nullable) */
+  float* query_out;       /* [B,N,256] */
+  float* importance_raw;  /* [B,N,N] */
+  float* pair_feat;       /* [B,2K,256] */
+  float* rel_feat;        /* [B,R,256] */
+  float* query_trace;     /* [layers,B,N,256] */
+  uint32_t* mask_trace;   /* [layers,B,N,trace_words] */
+  int trace_words;
+} PnHeadOutputs;
+
+PN_API size_t pn_head_workspace_bytes(const PnHeadWeights* w, const PnM2FInputs* in);
+PN_API int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const PnHeadOutputs* out,
+                    void* ws, size_t ws_bytes, pn_stream_t stream);
+/* number of kernels pn_head_forward enqueued on its last call on this thread */
+PN_API int pn_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAIRNET_B200_H_ */

@@ -1,0 +1,581 @@
+// C-ABI entry points (include/pairnet_b200.h) and the host-side orchestration of the kernel graph:
+// Mask2Former masked-attention decoder -> Pair Proposal Network -> Relation Fusion -> output gathers.
+// Everything is enqueued on the caller's stream with no synchronisation or allocation, so a whole
+// CrossHead2.forward is one CUDA-graph-capturable launch sequence.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pn {
+
+static thread_local char g_err[512] = "ok";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { ++g_launches; }
+int check_launch(const char* what) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+static int memset_async(void* p, int v, size_t bytes, cudaStream_t st) {
+  ++g_launches;
+  cudaError_t e = cudaMemsetAsync(p, v, bytes, st);
+  if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+static int copy_async(void* d, const void* s, size_t bytes, cudaStream_t st) {
+  ++g_launches;
+  cudaError_t e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+static int linear1(const float* A, int lda, const PnLinear& L, float* C, int ldc, int M, int N, int K, int relu,
+                   cudaStream_t st) {
+  GemmBatch b{};
+  b.p[0] = make_linear(A, lda, L.w, L.b, C, ldc, M, N, K, relu);
+  b.count = 1;
+  return launch_gemm(b, st);
+}
+
+// Linear-ReLU-Linear-ReLU-Linear on [M,256]
+static int mlp3(const float* x, const PnMlp3& m, float* t1, float* t2, float* y, int M, cudaStream_t st) {
+  PN_TRY(linear1(x, D, m.l[0], t1, D, M, D, D, 1, st));
+  PN_TRY(linear1(t1, D, m.l[1], t2, D, M, D, D, 1, st));
+  return linear1(t2, D, m.l[2], y, D, M, D, D, 0, st);
+}
+
+struct LayerScratch {
+  float *x1, *x2;       // [M,256]
+  float *qp;            // [M,256] projected cross-attn queries
+  float *att, *proj;    // [M,256]
+  float *qk;            // [M,512]
+  float *vv;            // [M,256]
+  float *ffh;           // [M,ffn]
+  float *parts;         // [FFN_SPLITS][M,256]
+  void* mha_ws; size_t mha_ws_bytes;
+};
+constexpr int FFN_SPLITS = 8;
+
+static size_t layer_scratch_take(Workspace& ws, LayerScratch& s, int M, int ffn, size_t mha_bytes) {
+  s.x1 = ws.take<float>((size_t)M * D);
+  s.x2 = ws.take<float>((size_t)M * D);
+  s.qp = ws.take<float>((size_t)M * D);
+  s.att = ws.take<float>((size_t)M * D);
+  s.proj = ws.take<float>((size_t)M * D);
+  s.qk = ws.take<float>((size_t)M * 2 * D);
+  s.vv = ws.take<float>((size_t)M * D);
+  s.ffh = ws.take<float>((size_t)M * ffn);
+  s.parts = ws.take<float>((size_t)FFN_SPLITS * M * D);
+  s.mha_ws = ws.take<char>(mha_bytes);
+  s.mha_ws_bytes = mha_bytes;
+  return ws.off;
+}
+
+// One mmcv BaseTransformerLayer (cross_attn, norm, self_attn, norm, ffn, norm), post-norm residuals.
+//   x [B*Nq,256] in/out (updated in place), xpos = x + qpos in/out.
+//   kproj/vproj: already projected cross-attention keys/values [B,Nk,256].
+static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos, const float* qpos, int B, int Nq,
+                         const float* kproj, const float* vproj, int Nk, const uint32_t* bits, int words,
+                         const int* rowany, const PnNorm* post_norm, float* xn, LayerScratch& s, cudaStream_t st) {
+  const int M = B * Nq;
+  PN_REQUIRE(ffn % (FFN_SPLITS * 32) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
+             FFN_SPLITS * 32);
+  // ---- cross attention: q = (x + qpos) Wq^T + bq
+  {
+    PnLinear q{L.cross_attn.in_proj_w, L.cross_attn.in_proj_b};
+    PN_TRY(linear1(xpos, D, q, s.qp, D, M, D, D, 0, st));
+    MhaArgs a{s.qp, D, kproj, D, vproj, D, bits, words, rowany, s.att, B, Nq, Nk};
+    PN_TRY(launch_mha(a, s.mha_ws, s.mha_ws_bytes, st));
+    PnLinear o{L.cross_attn.out_proj_w, L.cross_attn.out_proj_b};
+    PN_TRY(linear1(s.att, D, o, s.proj, D, M, D, D, 0, st));
+    LnArgs n{};
+    n.x = s.proj; n.nparts = 1; n.resid = x; n.gamma = L.norm[0].gamma; n.beta = L.norm[0].beta;
+    n.y = s.x1; n.pos = qpos; n.pos_mod = Nq; n.ypos = xpos; n.M = M;
+    PN_TRY(launch_layernorm(n, st));
+  }
+  // ---- self attention: q = k = (x1 + qpos) W{q,k}^T, v = x1 Wv^T
+  {
+    GemmBatch g{};
+    g.p[0] = make_linear(xpos, D, L.self_attn.in_proj_w, L.self_attn.in_proj_b, s.qk, 2 * D, M, 2 * D, D);
+    g.p[1] = make_linear(s.x1, D, L.self_attn.in_proj_w + (size_t)2 * D * D, L.self_attn.in_proj_b + 2 * D, s.vv, D,
+                         M, D, D);
+    g.count = 2;
+    PN_TRY(launch_gemm(g, st));
+    MhaArgs a{s.qk, 2 * D, s.qk + D, 2 * D, s.vv, D, nullptr, 0, nullptr, s.att, B, Nq, Nq};
+    PN_TRY(launch_mha(a, s.mha_ws, s.mha_ws_bytes, st));
+    PnLinear o{L.self_attn.out_proj_w, L.self_attn.out_proj_b};
+    PN_TRY(linear1(s.att, D, o, s.proj, D, M, D, D, 0, st));
+    LnArgs n{};
+    n.x = s.proj; n.nparts = 1; n.resid = s.x1; n.gamma = L.norm[1].gamma; n.beta = L.norm[1].beta;
+    n.y = s.x2; n.M = M;
+    PN_TRY(launch_layernorm(n, st));
+  }
+  // ---- FFN: x3 = LN(x2 + relu(x2 W1^T + b1) W2^T + b2), split-K partials reduced inside the LN
+  {
+    PN_TRY(linear1(s.x2, D, L.ffn1, s.ffh, ffn, M, ffn, D, 1, st));
+    GemmBatch g{};
+    g.p[0] = make_linear(s.ffh, ffn, L.ffn2.w, nullptr, s.parts, D, M, D, ffn);
+    g.p[0].splits = FFN_SPLITS;
+    g.p[0].split_stride = (long long)M * D;
+    g.count = 1;
+    PN_TRY(launch_gemm(g, st));
+    LnArgs n{};
+    n.x = s.parts; n.nparts = FFN_SPLITS; n.part_stride = (long long)M * D; n.bias = L.ffn2.b; n.resid = s.x2;
+    n.gamma = L.norm[2].gamma; n.beta = L.norm[2].beta;
+    n.y = x; n.pos = qpos; n.pos_mod = Nq; n.ypos = xpos; n.M = M;
+    if (post_norm) { n.gamma2 = post_norm->gamma; n.beta2 = post_norm->beta; n.y2 = xn; }
+    PN_TRY(launch_layernorm(n, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct M2FPlan {
+  int B, N, M, L, nl, ffn;
+  int hw[PN_MAX_LEVELS], ldf[PN_MAX_LEVELS];
+  int maxhw, maxldf;
+  size_t mha_bytes;
+};
+
+static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
+  PN_REQUIRE(w && in, PN_ERR_BAD_ARG, "m2f: null weights/inputs");
+  p.B = in->B; p.N = w->num_queries; p.M = p.B * p.N; p.L = w->num_levels; p.nl = w->num_layers; p.ffn = w->ffn_dims;
+  PN_REQUIRE(p.B > 0 && p.N > 0, PN_ERR_BAD_ARG, "m2f: bad B/N");
+  PN_REQUIRE(p.L >= 1 && p.L <= PN_MAX_LEVELS, PN_ERR_BAD_ARG, "m2f: num_levels out of range");
+  PN_REQUIRE(p.nl >= 1 && p.nl <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "m2f: num_layers out of range");
+  PN_REQUIRE(in->H4 > 0 && in->W4 > 0 && in->mask_features, PN_ERR_BAD_ARG, "m2f: bad mask_features");
+  p.maxhw = 0; p.maxldf = 0; p.mha_bytes = mha_workspace_bytes(p.B, p.N, p.N);
+  for (int l = 0; l < p.L; ++l) {
+    PN_REQUIRE(in->h[l] > 0 && in->w[l] > 0 && in->memory[l], PN_ERR_BAD_ARG, "m2f: bad level %d", l);
+    p.hw[l] = in->h[l] * in->w[l];
+    p.ldf[l] = (int)round_up(p.hw[l], 64);
+    p.maxhw = p.hw[l] > p.maxhw ? p.hw[l] : p.maxhw;
+    p.maxldf = p.ldf[l] > p.maxldf ? p.ldf[l] : p.maxldf;
+    size_t mb = mha_workspace_bytes(p.B, p.N, p.hw[l]);
+    p.mha_bytes = mb > p.mha_bytes ? mb : p.mha_bytes;
+  }
+  return 0;
+}
+
+struct M2FBuffers {
+  float *X[PN_MAX_LEVELS], *XP[PN_MAX_LEVELS], *Fl[PN_MAX_LEVELS], *pos[PN_MAX_LEVELS];
+  float *K, *V;
+  uint32_t* bits; int* rowany;
+  float *x, *xpos, *xn, *e1, *e2, *e;
+  LayerScratch ls;
+};
+
+static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2FBuffers& b) {
+  for (int l = 0; l < p.L; ++l) {
+    b.X[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
+    b.XP[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
+    b.Fl[l] = ws.take<float>((size_t)p.B * D * p.ldf[l]);
+    b.pos[l] = (in && in->pos[l]) ? nullptr : ws.take<float>((size_t)p.hw[l] * D);
+  }
+  b.K = ws.take<float>((size_t)p.B * p.maxhw * D);
+  b.V = ws.take<float>((size_t)p.B * p.maxhw * D);
+  b.bits = ws.take<uint32_t>((size_t)p.M * (p.maxldf / 32));
+  b.rowany = ws.take<int>((size_t)p.M);
+  b.x = ws.take<float>((size_t)p.M * D);
+  b.xpos = ws.take<float>((size_t)p.M * D);
+  b.xn = ws.take<float>((size_t)p.M * D);
+  b.e1 = ws.take<float>((size_t)p.M * D);
+  b.e2 = ws.take<float>((size_t)p.M * D);
+  b.e = ws.take<float>((size_t)p.M * D);
+  layer_scratch_take(ws, b.ls, p.M, p.ffn, p.mha_bytes);
+}
+
+static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2FOutputs* out, Workspace& ws,
+                       cudaStream_t st) {
+  M2FPlan p;
+  PN_TRY(m2f_plan(w, in, p));
+  PN_REQUIRE(out && out->cls_pred && out->mask_pred, PN_ERR_BAD_ARG, "m2f: null outputs");
+  M2FBuffers b{};
+  m2f_take(ws, p, in, b);
+  PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "m2f: workspace too small (%zu needed so far, %zu given)", ws.off,
+             ws.cap);
+  const int HW4 = in->H4 * in->W4;
+
+  // ---- row 1 + the linear half of row 2 that does not depend on the queries
+  for (int l = 0; l < p.L; ++l) {
+    const float* pos = in->pos[l];
+    if (!pos) {
+      PN_TRY(launch_sine_posenc(b.pos[l], in->h[l], in->w[l], st));
+      pos = b.pos[l];
+    }
+    PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st));
+    PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
+                                      st));
+  }
+  // ---- learned queries (pairnet_head.py:290-291) and post_norm for the first head call
+  PN_TRY(launch_bcast_rows(w->query_feat, w->query_embed, b.x, b.xpos, p.B, p.N, st));
+  {
+    LnArgs n{};
+    n.x = b.x; n.nparts = 1; n.gamma = w->post_norm.gamma; n.beta = w->post_norm.beta; n.y = b.xn; n.M = p.M;
+    PN_TRY(launch_layernorm(n, st));
+  }
+  for (int i = 0; i < p.nl; ++i) {
+    const int l = i % p.L;
+    const PnDecoderLayer& Lw = w->layers[i];
+    const int words = p.ldf[l] / 32;
+    // forward_head (mask branch only): attn_mask = (mask_embed(post_norm(x)) . resize(F) < 0)
+    PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, st));
+    PN_TRY(memset_async(b.rowany, 0, sizeof(int) * p.M, st));
+    PN_TRY(launch_gemm_nmajor_maskbits(b.e, b.Fl[l], b.bits, b.rowany, p.B, p.N, p.hw[l], p.ldf[l], st));
+    if (out->mask_trace) {
+      PN_REQUIRE(out->trace_words >= words, PN_ERR_BAD_ARG, "m2f: trace_words too small");
+      ++g_launches;
+      cudaError_t e = cudaMemcpy2DAsync(out->mask_trace + (size_t)i * p.M * out->trace_words,
+                                        (size_t)out->trace_words * 4, b.bits, (size_t)words * 4, (size_t)words * 4,
+                                        p.M, cudaMemcpyDeviceToDevice, st);
+      PN_REQUIRE(e == cudaSuccess, (int)e, "mask trace copy: %s", cudaGetErrorString(e));
+    }
+    // K/V projections of this layer's memory level: k = (mem + lvl + pos) Wk^T, v = (mem + lvl) Wv^T
+    {
+      const int Mk = p.B * p.hw[l];
+      GemmBatch g{};
+      g.p[0] = make_linear(b.XP[l], D, Lw.cross_attn.in_proj_w + (size_t)D * D, Lw.cross_attn.in_proj_b + D, b.K, D,
+                           Mk, D, D);
+      g.p[1] = make_linear(b.X[l], D, Lw.cross_attn.in_proj_w + (size_t)2 * D * D, Lw.cross_attn.in_proj_b + 2 * D,
+                           b.V, D, Mk, D, D);
+      g.count = 2;
+      PN_TRY(launch_gemm(g, st));
+    }
+    PN_TRY(decoder_layer(Lw, p.ffn, b.x, b.xpos, w->query_embed, p.B, p.N, b.K, b.V, p.hw[l], b.bits, words,
+                         b.rowany, &w->post_norm, b.xn, b.ls, st));
+    if (out->query_trace) PN_TRY(copy_async(out->query_trace + (size_t)i * p.M * D, b.x, sizeof(float) * p.M * D, st));
+  }
+  // ---- last forward_head: cls_pred + full-resolution mask_pred (the only ones that are outputs)
+  PN_TRY(linear1(b.xn, D, w->cls_embed, out->cls_pred, w->num_cls, p.M, w->num_cls, D, 0, st));
+  PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, st));
+  {
+    GemmProb g = make_linear(b.e, D, in->mask_features, nullptr, out->mask_pred, HW4, p.N, HW4, D);
+    g.ldw = HW4;
+    g.nb = p.B; g.sA = (long long)p.N * D; g.sW = (long long)D * HW4; g.sC = (long long)p.N * HW4;
+    PN_TRY(launch_gemm_nmajor_store(g, st));
+  }
+  if (out->query_out) PN_TRY(copy_async(out->query_out, b.x, sizeof(float) * p.M * D, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int ppn_forward(const float* query, const float* query_obj, const PnMlp3* sub_mlp, const PnMlp3* obj_mlp,
+                       const PnConvTiny* conv, float* importance_raw, float* importance, int64_t* topk_idx,
+                       int64_t* sub_pos, int64_t* obj_pos, float* pair_feat, int B, int N, int K, Workspace& ws,
+                       cudaStream_t st) {
+  PN_REQUIRE(query && importance && sub_pos && obj_pos, PN_ERR_BAD_ARG, "ppn: null pointer");
+  PN_REQUIRE((sub_mlp != nullptr) == (obj_mlp != nullptr), PN_ERR_BAD_ARG, "ppn: sub/obj MLP must come together");
+  PN_REQUIRE(sub_mlp ? query_obj == nullptr : query_obj != nullptr, PN_ERR_BAD_ARG,
+             "ppn: query_obj is only for the MLP-less microbenchmark mode");
+  const int M = B * N;
+  const float *S = query, *O = query_obj;
+  float* h1 = nullptr; float* h2 = nullptr; float* emb = nullptr; float* nrm = nullptr;
+  if (sub_mlp) {
+    h1 = ws.take<float>((size_t)2 * M * D);
+    h2 = ws.take<float>((size_t)2 * M * D);
+    emb = ws.take<float>((size_t)2 * M * D);
+    nrm = ws.take<float>((size_t)2 * M * D);
+  }
+  float* raw = importance_raw;
+  if (!raw) raw = conv ? ws.take<float>((size_t)B * N * N) : importance;
+  const size_t conv_bytes = conv ? conv_tiny_workspace_bytes(B, N, conv->mid_channels) : 0;
+  char* conv_ws = conv ? ws.take<char>(conv_bytes) : nullptr;
+  PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "ppn: workspace too small");
+
+  if (sub_mlp) {
+    // rows 4: only the last decoder layer's output feeds the pair matrix (pairnet_head.py:325-326)
+    const float* in[2] = {query, query};
+    float* bufs[3] = {h1, h2, emb};
+    for (int s = 0; s < 3; ++s) {
+      GemmBatch g{};
+      for (int t = 0; t < 2; ++t) {
+        const PnMlp3* m = t == 0 ? sub_mlp : obj_mlp;
+        g.p[t] = make_linear(in[t], D, m->l[s].w, m->l[s].b, bufs[s] + (size_t)t * M * D, D, M, D, D, s < 2 ? 1 : 0);
+      }
+      g.count = 2;
+      PN_TRY(launch_gemm(g, st));
+      in[0] = bufs[s];
+      in[1] = bufs[s] + (size_t)M * D;
+    }
+    PN_TRY(launch_l2norm(emb, nrm, 2 * M, st));
+    S = nrm;
+    O = nrm + (size_t)M * D;
+  }
+  {  // row 5: importance_raw[b] = S[b] O[b]^T
+    GemmBatch g{};
+    g.p[0] = make_linear(S, D, O, nullptr, raw, N, N, N, D);
+    g.p[0].nb = B; g.p[0].sA = (long long)N * D; g.p[0].sW = (long long)N * D; g.p[0].sC = (long long)N * N;
+    g.count = 1;
+    PN_TRY(launch_gemm(g, st));
+  }
+  if (conv) {
+    PN_TRY(launch_conv_tiny(raw, conv, importance, B, N, conv_ws, conv_bytes, st));
+  } else if (raw != importance) {
+    PN_TRY(copy_async(importance, raw, sizeof(float) * B * N * N, st));
+  }
+  return launch_topk_pairs(importance, topk_idx, sub_pos, obj_pos, query, pair_feat, B, N, K, st);
+}
+
+static size_t ppn_bytes(int B, int N, int K, int mid) {
+  Workspace ws(nullptr, 0);
+  const int M = B * N;
+  for (int i = 0; i < 4; ++i) ws.take<float>((size_t)2 * M * D);
+  ws.take<float>((size_t)B * N * N);
+  ws.take<char>(conv_tiny_workspace_bytes(B, N, mid > 0 ? mid : 64));
+  return ws.off + 1024;
+}
+
+// ------------------------------------------------------------------------------------------------
+static void rel_take(Workspace& ws, int B, int R, int K2, int nl, int ffn, float** x, float** xpos, float** pk,
+                     float** Kall, float** Vall, LayerScratch& ls) {
+  const int M = B * R, Mk = B * K2;
+  *x = ws.take<float>((size_t)M * D);
+  *xpos = ws.take<float>((size_t)M * D);
+  *pk = ws.take<float>((size_t)Mk * D);
+  *Kall = ws.take<float>((size_t)nl * Mk * D);
+  *Vall = ws.take<float>((size_t)nl * Mk * D);
+  size_t mb = mha_workspace_bytes(B, R, K2);
+  size_t mb2 = mha_workspace_bytes(B, R, R);
+  layer_scratch_take(ws, ls, M, ffn, mb > mb2 ? mb : mb2);
+}
+
+static int rel_forward(const PnRelWeights* w, const float* pair_feat, float* rel_preds, float* rel_feat_out, int B,
+                       int K2, Workspace& ws, cudaStream_t st) {
+  PN_REQUIRE(w && pair_feat && rel_preds, PN_ERR_BAD_ARG, "relation_fusion: null pointer");
+  const int R = w->num_rel_queries, nl = w->num_layers, ffn = w->ffn_dims;
+  PN_REQUIRE(R > 0 && K2 > 0 && B > 0 && nl >= 1 && nl <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "relation_fusion: bad sizes");
+  const int M = B * R, Mk = B * K2;
+  float *x, *xpos, *pk, *Kall, *Vall;
+  LayerScratch ls;
+  rel_take(ws, B, R, K2, nl, ffn, &x, &xpos, &pk, &Kall, &Vall, ls);
+  PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "relation_fusion: workspace too small");
+
+  PN_TRY(launch_bcast_rows(w->rel_query_feat, w->rel_query_embed, x, xpos, B, R, st));
+  PN_TRY(launch_add_rows(pair_feat, w->rel_query_embed2, pk, B, K2, st));
+  // K/V of every layer up front: pair_feat does not change across layers (pairnet_head.py:365-376)
+  for (int l0 = 0; l0 < nl; l0 += GEMM_MAX_PROBS / 2) {
+    GemmBatch g{};
+    int c = 0;
+    for (int l = l0; l < nl && c + 2 <= GEMM_MAX_PROBS; ++l) {
+      const PnMHA& a = w->layers[l].cross_attn;
+      g.p[c++] = make_linear(pk, D, a.in_proj_w + (size_t)D * D, a.in_proj_b + D, Kall + (size_t)l * Mk * D, D, Mk, D, D);
+      g.p[c++] = make_linear(pair_feat, D, a.in_proj_w + (size_t)2 * D * D, a.in_proj_b + 2 * D,
+                             Vall + (size_t)l * Mk * D, D, Mk, D, D);
+    }
+    g.count = c;
+    PN_TRY(launch_gemm(g, st));
+  }
+  for (int l = 0; l < nl; ++l) {
+    PN_TRY(decoder_layer(w->layers[l], ffn, x, xpos, w->rel_query_embed, B, R, Kall + (size_t)l * Mk * D,
+                         Vall + (size_t)l * Mk * D, K2, nullptr, 0, nullptr, nullptr, nullptr, ls, st));
+  }
+  PN_TRY(linear1(x, D, w->rel_cls_embed, rel_preds, w->num_rel_cls, M, w->num_rel_cls, D, 0, st));
+  if (rel_feat_out) PN_TRY(copy_async(rel_feat_out, x, sizeof(float) * M * D, st));
+  return 0;
+}
+
+}  // namespace pn
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+using namespace pn;
+
+extern "C" {
+
+int pn_version(void) { return PN_VERSION; }
+const char* pn_last_error_string(void) { return g_err; }
+int pn_last_launch_count(void) { return g_launches; }
+
+int pn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("pn_device_info: %s", cudaGetErrorString(e)); return (int)e; }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+int pn_sine_posenc(float* pos, int h, int w, pn_stream_t stream) { return launch_sine_posenc(pos, h, w, as_stream(stream)); }
+
+int pn_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp, int B, int hw,
+                  pn_stream_t stream) {
+  return launch_level_prep(mem, level_embed, pos, x, xp, B, hw, as_stream(stream));
+}
+
+int pn_mask_feature_resize(const float* mask_feature, float* out, int B, int H, int W, int h, int w, int ldo,
+                           pn_stream_t stream) {
+  return launch_mask_feature_resize(mask_feature, out, B, H, W, h, w, ldo, as_stream(stream));
+}
+
+int pn_attn_mask_bits(const float* E, const float* F, uint32_t* bits, int* rowany, int B, int N, int hw, int ldf,
+                      pn_stream_t stream) {
+  return launch_gemm_nmajor_maskbits(E, F, bits, rowany, B, N, hw, ldf, as_stream(stream));
+}
+
+int pn_mask_pred(const float* E, const float* F, float* mask_pred, int B, int N, int HW, pn_stream_t stream) {
+  PN_REQUIRE(E && F && mask_pred && B > 0 && N > 0 && HW > 0, PN_ERR_BAD_ARG, "mask_pred: bad args");
+  GemmProb g = make_linear(E, D, F, nullptr, mask_pred, HW, N, HW, D);
+  g.ldw = HW;
+  g.nb = B; g.sA = (long long)N * D; g.sW = (long long)D * HW; g.sC = (long long)N * HW;
+  return launch_gemm_nmajor_store(g, as_stream(stream));
+}
+
+int pn_linear(const float* x, int ldx, const float* w, const float* b, const float* resid, float* y, int ldy, int M,
+              int N, int K, int relu, pn_stream_t stream) {
+  GemmBatch g{};
+  g.p[0] = make_linear(x, ldx, w, b, y, ldy, M, N, K, relu, resid, ldy);
+  g.count = 1;
+  return launch_gemm(g, as_stream(stream));
+}
+
+int pn_add_layernorm(const float* x, const float* resid, const float* gamma, const float* beta, float* y, int M,
+                     pn_stream_t stream) {
+  LnArgs n{};
+  n.x = x; n.nparts = 1; n.resid = resid; n.gamma = gamma; n.beta = beta; n.y = y; n.M = M;
+  return launch_layernorm(n, as_stream(stream));
+}
+
+size_t pn_mha_workspace_bytes(int B, int Nq, int Nk) { return mha_workspace_bytes(B, Nq, Nk); }
+
+int pn_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const uint32_t* mask_bits,
+                int mask_words, const int* rowany, float* out, int B, int Nq, int Nk, void* ws, size_t ws_bytes,
+                pn_stream_t stream) {
+  MhaArgs a{q, ldq, k, ldk, v, ldv, mask_bits, mask_words, rowany, out, B, Nq, Nk};
+  return launch_mha(a, ws, ws_bytes, as_stream(stream));
+}
+
+size_t pn_m2f_decoder_workspace_bytes(const PnM2FWeights* w, const PnM2FInputs* in) {
+  M2FPlan p;
+  if (m2f_plan(w, in, p) != 0) return 0;
+  Workspace ws(nullptr, 0);
+  M2FBuffers b{};
+  m2f_take(ws, p, nullptr, b);
+  return ws.off + 1024;
+}
+
+int pn_m2f_decoder_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2FOutputs* out, void* ws,
+                           size_t ws_bytes, pn_stream_t stream) {
+  g_launches = 0;
+  PN_REQUIRE(ws, PN_ERR_WORKSPACE, "m2f: null workspace");
+  Workspace W(ws, ws_bytes);
+  return m2f_forward(w, in, out, W, as_stream(stream));
+}
+
+size_t pn_ppn_workspace_bytes(int B, int N, int K, int mid_channels) { return ppn_bytes(B, N, K, mid_channels); }
+
+int pn_ppn_forward(const float* query, const float* query_obj, const PnMlp3* sub_mlp, const PnMlp3* obj_mlp,
+                   const PnConvTiny* conv, float* importance_raw, float* importance, int64_t* topk_idx,
+                   int64_t* sub_pos, int64_t* obj_pos, float* pair_feat, int B, int N, int K, void* ws,
+                   size_t ws_bytes, pn_stream_t stream) {
+  g_launches = 0;
+  PN_REQUIRE(ws, PN_ERR_WORKSPACE, "ppn: null workspace");
+  Workspace W(ws, ws_bytes);
+  return ppn_forward(query, query_obj, sub_mlp, obj_mlp, conv, importance_raw, importance, topk_idx, sub_pos, obj_pos,
+                     pair_feat, B, N, K, W, as_stream(stream));
+}
+
+int pn_conv_tiny(const float* x, const PnConvTiny* conv, float* y, int B, int N, void* ws, size_t ws_bytes,
+                 pn_stream_t stream) {
+  return launch_conv_tiny(x, conv, y, B, N, ws, ws_bytes, as_stream(stream));
+}
+
+int pn_topk_pairs(const float* importance, int64_t* topk_idx, int64_t* sub_pos, int64_t* obj_pos, const float* query,
+                  float* pair_feat, int B, int N, int K, pn_stream_t stream) {
+  return launch_topk_pairs(importance, topk_idx, sub_pos, obj_pos, query, pair_feat, B, N, K, as_stream(stream));
+}
+
+size_t pn_relation_fusion_workspace_bytes(int B, int R, int K2, int ffn_dims) {
+  Workspace ws(nullptr, 0);
+  float *a, *b, *c, *d, *e;
+  LayerScratch ls;
+  rel_take(ws, B, R, K2, PN_MAX_LAYERS, ffn_dims, &a, &b, &c, &d, &e, ls);
+  return ws.off + 1024;
+}
+
+int pn_relation_fusion_forward(const PnRelWeights* w, const float* pair_feat, float* rel_preds, float* rel_feat_out,
+                               int B, int K2, void* ws, size_t ws_bytes, pn_stream_t stream) {
+  g_launches = 0;
+  PN_REQUIRE(ws, PN_ERR_WORKSPACE, "relation_fusion: null workspace");
+  Workspace W(ws, ws_bytes);
+  return rel_forward(w, pair_feat, rel_preds, rel_feat_out, B, K2, W, as_stream(stream));
+}
+
+int pn_gather_rows(const float* src, const int64_t* idx, float* dst, int B, int Nsrc, int R, long long L,
+                   pn_stream_t stream) {
+  return launch_gather_rows(src, idx, dst, B, Nsrc, R, L, as_stream(stream));
+}
+
+size_t pn_head_workspace_bytes(const PnHeadWeights* w, const PnM2FInputs* in) {
+  if (!w || !in) return 0;
+  const size_t a = pn_m2f_decoder_workspace_bytes(&w->m2f, in);
+  if (a == 0) return 0;
+  const int B = in->B, N = w->m2f.num_queries, R = w->rel.num_rel_queries;
+  const size_t b = ppn_bytes(B, N, R, w->update_importance.mid_channels);
+  const size_t c = pn_relation_fusion_workspace_bytes(B, R, 2 * R, w->rel.ffn_dims);
+  // stage scratch is reused (max), persistent taps are extra
+  size_t stage = a > b ? a : b;
+  stage = stage > c ? stage : c;
+  const size_t persist = ((size_t)B * N * D * 4 + 255 + (size_t)B * 2 * R * D * 4 + 255) + 1024;
+  return stage + persist;
+}
+
+int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const PnHeadOutputs* out, void* ws,
+                    size_t ws_bytes, pn_stream_t stream) {
+  g_launches = 0;
+  PN_REQUIRE(w && in && out && ws, PN_ERR_BAD_ARG, "head: null argument");
+  PN_REQUIRE(out->cls && out->mask && out->importance && out->rel && out->sub_pos && out->obj_pos, PN_ERR_BAD_ARG,
+             "head: required output pointer is null");
+  cudaStream_t st = as_stream(stream);
+  const int B = in->B, N = w->m2f.num_queries, R = w->rel.num_rel_queries, K = R;
+  const int HW4 = in->H4 * in->W4;
+  PN_REQUIRE(ws_bytes >= pn_head_workspace_bytes(w, in), PN_ERR_WORKSPACE, "head: workspace too small (%zu < %zu)",
+             ws_bytes, pn_head_workspace_bytes(w, in));
+  // persistent (cross-stage) buffers first, then per-stage scratch that each stage re-carves
+  Workspace P(ws, ws_bytes);
+  float* query = out->query_out ? out->query_out : P.take<float>((size_t)B * N * D);
+  float* pair = out->pair_feat ? out->pair_feat : P.take<float>((size_t)B * 2 * K * D);
+  char* stage = (char*)ws + P.off;
+  const size_t stage_bytes = ws_bytes - P.off;
+
+  {
+    PnM2FOutputs mo{};
+    mo.query_out = query; mo.cls_pred = out->cls; mo.mask_pred = out->mask;
+    mo.query_trace = out->query_trace; mo.mask_trace = out->mask_trace; mo.trace_words = out->trace_words;
+    Workspace W(stage, stage_bytes);
+    PN_TRY(m2f_forward(&w->m2f, in, &mo, W, st));
+  }
+  {
+    Workspace W(stage, stage_bytes);
+    PN_TRY(ppn_forward(query, nullptr, &w->sub_query_update, &w->obj_query_update, &w->update_importance,
+                       out->importance_raw, out->importance, nullptr, out->sub_pos, out->obj_pos, pair, B, N, K, W, st));
+  }
+  {
+    Workspace W(stage, stage_bytes);
+    PN_TRY(rel_forward(&w->rel, pair, out->rel, out->rel_feat, B, 2 * K, W, st));
+  }
+  // row 11 (pairnet_head.py:380-403)
+  if (out->sub) PN_TRY(launch_gather_rows(out->cls, out->sub_pos, out->sub, B, N, K, w->m2f.num_cls, st));
+  if (out->obj) PN_TRY(launch_gather_rows(out->cls, out->obj_pos, out->obj, B, N, K, w->m2f.num_cls, st));
+  if (out->sub_seg) PN_TRY(launch_gather_rows(out->mask, out->sub_pos, out->sub_seg, B, N, K, HW4, st));
+  if (out->obj_seg) PN_TRY(launch_gather_rows(out->mask, out->obj_pos, out->obj_seg, B, N, K, HW4, st));
+  return 0;
+}
+
+}  // extern "C"

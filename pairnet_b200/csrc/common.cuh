@@ -1,0 +1,138 @@
+// Shared helpers for the pairnet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pairnet_b200.h"
+
+namespace pn {
+
+constexpr int D = PN_EMBED_DIMS;  // 256
+constexpr int HD = PN_HEAD_DIM;   // 32
+constexpr int NH = D / HD;        // 8
+
+// ---- error plumbing (thread-local last error string + launch counter) -------------------------
+void set_error(const char* fmt, ...);
+void count_launch();
+int check_launch(const char* what);  // cudaGetLastError -> 0 / cudaError_t, records the string
+
+#define PN_REQUIRE(cond, code, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      pn::set_error(__VA_ARGS__);              \
+      return (code);                           \
+    }                                          \
+  } while (0)
+
+#define PN_TRY(expr)                 \
+  do {                               \
+    int _pn_rc = (expr);             \
+    if (_pn_rc != 0) return _pn_rc;  \
+  } while (0)
+
+static inline cudaStream_t as_stream(pn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---- bump allocator over the caller's workspace ------------------------------------------------
+struct Workspace {
+  char* base;
+  size_t cap;
+  size_t off;
+  bool dry;  // dry run: only measure
+  Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), dry(p == nullptr) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    if (dry) return nullptr;
+    if (off > cap) return nullptr;
+    return reinterpret_cast<T*>(base + o);
+  }
+  bool ok() const { return dry || off <= cap; }
+};
+
+// ---- grouped GEMM descriptors ------------------------------------------------------------------
+// C[b][m,n] = act( sum_k A[b][m,k] * Bop[b] + bias[n] ) + resid[m,n]
+//   B_KMAJOR  (linear):  Bop = W[n,k]   (W row-major [N,K], torch Linear layout)
+//   B_NMAJOR  (einsum):  Bop = F[k,n]   (F row-major [K,N])
+struct GemmProb {
+  const float* A;
+  const float* W;
+  const float* bias;
+  const float* resid;
+  float* C;
+  int M, N, K;
+  int lda, ldw, ldc, ldr;
+  int relu;
+  int nb;                       // strided batch count (>=1)
+  long long sA, sW, sC, sR;     // batch strides (elements)
+  int splits;                   // split-K (>=1); partial s goes to C + s*split_stride, no epilogue
+  long long split_stride;
+};
+constexpr int GEMM_MAX_PROBS = 12;
+struct GemmBatch {
+  GemmProb p[GEMM_MAX_PROBS];
+  int count;
+};
+
+GemmProb make_linear(const float* A, int lda, const float* W, const float* bias, float* C, int ldc,
+                     int M, int N, int K, int relu = 0, const float* resid = nullptr, int ldr = 0);
+
+// launchers (all return 0 / error code)
+int launch_gemm(const GemmBatch& batch, cudaStream_t st);                      // B K-major
+int launch_gemm_nmajor_store(const GemmProb& p, cudaStream_t st);              // einsum, fp32 store
+int launch_gemm_nmajor_maskbits(const float* E, const float* F, uint32_t* bits, int* rowany, int B,
+                                int N, int hw, int ldf, cudaStream_t st);
+
+struct LnArgs {
+  const float* x;          // [nparts][M][256]
+  int nparts;
+  long long part_stride;
+  const float* bias;       // [256] or null
+  const float* resid;      // [M][256] or null
+  const float* gamma;
+  const float* beta;
+  float* y;                // LN output
+  const float* pos;        // [pos_mod][256] or null
+  int pos_mod;
+  float* ypos;             // y + pos[m % pos_mod] or null
+  const float* gamma2;     // optional chained second LN (post_norm)
+  const float* beta2;
+  float* y2;
+  int M;
+};
+int launch_layernorm(const LnArgs& a, cudaStream_t st);
+
+struct MhaArgs {
+  const float* q; int ldq;
+  const float* k; int ldk;
+  const float* v; int ldv;
+  const uint32_t* mask_bits; int mask_words;
+  const int* rowany;
+  float* out;       // [B,Nq,256]
+  int B, Nq, Nk;
+};
+size_t mha_workspace_bytes(int B, int Nq, int Nk);
+int launch_mha(const MhaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+
+int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
+int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
+                      int B, int hw, cudaStream_t st);
+int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
+                               cudaStream_t st);
+int launch_bcast_rows(const float* a, const float* b, float* out, float* out_sum, int B, int N,
+                      cudaStream_t st);
+int launch_add_rows(const float* x, const float* pos, float* out, int B, int N, cudaStream_t st);
+int launch_l2norm(const float* x, float* y, int M, cudaStream_t st);
+int launch_gather_rows(const float* src, const int64_t* idx, float* dst, int B, int Nsrc, int R,
+                       long long L, cudaStream_t st);
+int launch_conv_tiny(const float* x, const PnConvTiny* conv, float* y, int B, int N, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+size_t conv_tiny_workspace_bytes(int B, int N, int mid);
+int launch_topk_pairs(const float* imp, int64_t* topk_idx, int64_t* sub_pos, int64_t* obj_pos,
+                      const float* query, float* pair_feat, int B, int N, int K, cudaStream_t st);
+
+}  // namespace pn

@@ -1,0 +1,285 @@
+// Row-wise / bandwidth-bound kernels: fused (split-K reduce + bias + residual + LayerNorm
+// [+ query_pos add] [+ chained post_norm]), L2 normalise, learned-query broadcast, level prep
+// (transpose + level_embed + sine positional encoding), bilinear mask-feature resize, row gathers.
+// All are HBM/L2-bound: one warp per 256-channel row, 128-bit accesses, grid sized to the rows.
+#include "common.cuh"
+
+namespace pn {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void ln_row(float (&v)[8], const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float var = warp_sum(q) * (1.f / D);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 32 + lane);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 32 + lane);
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + bb[i];
+}
+
+__device__ __forceinline__ void load_row(float (&v)[8], const float* __restrict__ p, int lane) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + lane);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 32 + lane);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store_row(const float (&v)[8], float* __restrict__ p, int lane) {
+  reinterpret_cast<float4*>(p)[lane] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// lane owns channels [4*lane, 4*lane+4) and [128+4*lane, 128+4*lane+4)
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= a.M) return;
+  float v[8];
+  load_row(v, a.x + (size_t)m * D, lane);
+  for (int s = 1; s < a.nparts; ++s) {  // fixed order -> deterministic split-K reduction
+    float t[8];
+    load_row(t, a.x + (size_t)s * a.part_stride + (size_t)m * D, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+  }
+  if (a.bias) {
+    float t[8];
+    load_row(t, a.bias, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+  }
+  if (a.resid) {
+    float t[8];
+    load_row(t, a.resid + (size_t)m * D, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[i] + v[i];
+  }
+  ln_row(v, a.gamma, a.beta, lane);
+  store_row(v, a.y + (size_t)m * D, lane);
+  if (a.ypos) {
+    float t[8];
+    load_row(t, a.pos + (size_t)(m % a.pos_mod) * D, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = v[i] + t[i];
+    store_row(t, a.ypos + (size_t)m * D, lane);
+  }
+  if (a.y2) {
+    ln_row(v, a.gamma2, a.beta2, lane);
+    store_row(v, a.y2 + (size_t)m * D, lane);
+  }
+}
+
+int launch_layernorm(const LnArgs& a, cudaStream_t st) {
+  PN_REQUIRE(a.x && a.gamma && a.beta && a.y && a.M > 0 && a.nparts >= 1, PN_ERR_BAD_ARG, "layernorm: bad args");
+  PN_REQUIRE(!a.ypos || (a.pos && a.pos_mod > 0), PN_ERR_BAD_ARG, "layernorm: ypos needs pos");
+  PN_REQUIRE(!a.y2 || (a.gamma2 && a.beta2), PN_ERR_BAD_ARG, "layernorm: y2 needs gamma2/beta2");
+  layernorm_kernel<<<cdiv(a.M, 8), 256, 0, st>>>(a);
+  return check_launch("layernorm_kernel");
+}
+
+// F.normalize(x, p=2, dim=-1, eps=1e-12): x / max(||x||_2, eps)      (pairnet_head.py:325-326)
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, int M) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float v[8];
+  load_row(v, x + (size_t)m * D, lane);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q += v[i] * v[i];
+  const float nrm = fmaxf(sqrtf(warp_sum(q)), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] / nrm;
+  store_row(v, y + (size_t)m * D, lane);
+}
+int launch_l2norm(const float* x, float* y, int M, cudaStream_t st) {
+  l2norm_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, y, M);
+  return check_launch("l2norm_kernel");
+}
+
+// out[b,n,:] = a[n,:] ; out_sum[b,n,:] = a[n,:] + b[n,:]   (learned queries repeated per image)
+__global__ void __launch_bounds__(256) bcast_rows_kernel(const float* __restrict__ a, const float* __restrict__ bpos,
+                                                          float* __restrict__ out, float* __restrict__ out_sum,
+                                                          int B, int N) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= B * N) return;
+  const int n = m % N;
+  float v[8];
+  load_row(v, a + (size_t)n * D, lane);
+  if (out) store_row(v, out + (size_t)m * D, lane);
+  if (out_sum) {
+    float t[8];
+    load_row(t, bpos + (size_t)n * D, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = v[i] + t[i];
+    store_row(t, out_sum + (size_t)m * D, lane);
+  }
+}
+int launch_bcast_rows(const float* a, const float* b, float* out, float* out_sum, int B, int N, cudaStream_t st) {
+  bcast_rows_kernel<<<cdiv((long long)B * N, 8), 256, 0, st>>>(a, b, out, out_sum, B, N);
+  return check_launch("bcast_rows_kernel");
+}
+
+// out[b,n,:] = x[b,n,:] + pos[n,:]
+__global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                                        float* __restrict__ out, int B, int N) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= B * N) return;
+  float v[8], t[8];
+  load_row(v, x + (size_t)m * D, lane);
+  load_row(t, pos + (size_t)(m % N) * D, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] + t[i];
+  store_row(v, out + (size_t)m * D, lane);
+}
+int launch_add_rows(const float* x, const float* pos, float* out, int B, int N, cudaStream_t st) {
+  add_rows_kernel<<<cdiv((long long)B * N, 8), 256, 0, st>>>(x, pos, out, B, N);
+  return check_launch("add_rows_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// mmdet SinePositionalEncoding(num_feats=128, normalize=True, temperature=1e4, scale=2pi,
+// eps=1e-6, offset=0) of an all-false mask, written token-major [h*w, 256]:
+// channels [0,128) = pos_y, [128,256) = pos_x; even channel -> sin, odd -> cos.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sine_posenc_kernel(float* __restrict__ pos, int h, int w) {
+  const int p = blockIdx.x;
+  const int c = threadIdx.x;
+  const int y = p / w, x = p % w;
+  const float scale = 6.283185307179586f;  // float32(2*pi)
+  const bool is_x = c >= 128;
+  const int i = c & 127;
+  const float embed = is_x ? ((float)(x + 1) / ((float)w + 1e-6f)) * scale
+                           : ((float)(y + 1) / ((float)h + 1e-6f)) * scale;
+  const float expo = (float)(2 * (i / 2)) / 128.f;
+  const float dim_t = (float)pow(10000.0, (double)expo);
+  const float arg = embed / dim_t;
+  pos[(size_t)p * D + c] = (i & 1) ? cosf(arg) : sinf(arg);
+}
+int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st) {
+  PN_REQUIRE(pos && h > 0 && w > 0, PN_ERR_BAD_ARG, "sine_posenc: bad args");
+  sine_posenc_kernel<<<h * w, 256, 0, st>>>(pos, h, w);
+  return check_launch("sine_posenc_kernel");
+}
+
+// mem [B,256,hw] -> x [B,hw,256] (+ level_embed) ; xp = x + pos.   32x32 smem transpose tiles.
+__global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict__ mem,
+                                                          const float* __restrict__ level_embed,
+                                                          const float* __restrict__ pos, float* __restrict__ x,
+                                                          float* __restrict__ xp, int hw) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* src = mem + (size_t)b * D * hw;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + r * 8, p = p0 + tx;
+    tile[ty + r * 8][tx] = (p < hw) ? __ldg(src + (size_t)c * hw + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + r * 8, c = c0 + tx;
+    if (p < hw) {
+      const float v = tile[tx][ty + r * 8] + __ldg(level_embed + c);
+      const size_t o = ((size_t)b * hw + p) * D + c;
+      x[o] = v;
+      xp[o] = v + __ldg(pos + (size_t)p * D + c);
+    }
+  }
+}
+int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp, int B,
+                      int hw, cudaStream_t st) {
+  PN_REQUIRE(mem && level_embed && pos && x && xp && B > 0 && hw > 0, PN_ERR_BAD_ARG, "level_prep: bad args");
+  dim3 grid(cdiv(hw, 32), D / 32, B);
+  level_prep_kernel<<<grid, 256, 0, st>>>(mem, level_embed, pos, x, xp, hw);
+  return check_launch("level_prep_kernel");
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) of [B,256,H,W] to (h,w); rows padded to ldo.
+__global__ void __launch_bounds__(256) mask_feature_resize_kernel(const float* __restrict__ F,
+                                                                   float* __restrict__ out, int H, int W, int h,
+                                                                   int w, int ldo, float sh, float sw) {
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  const size_t plane = blockIdx.y;  // b*256 + c
+  if (o >= ldo) return;
+  float r = 0.f;
+  if (o < h * w) {
+    const int oy = o / w, ox = o % w;
+    float sy = sh * ((float)oy + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    float sx = sw * ((float)ox + 0.5f) - 0.5f;
+    sx = sx < 0.f ? 0.f : sx;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int yp = (y0 < H - 1) ? 1 : 0, xq = (x0 < W - 1) ? 1 : 0;
+    const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+    const float* src = F + plane * (size_t)H * W;
+    const float v00 = __ldg(src + (size_t)y0 * W + x0), v01 = __ldg(src + (size_t)y0 * W + x0 + xq);
+    const float v10 = __ldg(src + (size_t)(y0 + yp) * W + x0), v11 = __ldg(src + (size_t)(y0 + yp) * W + x0 + xq);
+    r = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  }
+  out[plane * (size_t)ldo + o] = r;
+}
+int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
+                               cudaStream_t st) {
+  PN_REQUIRE(F && out && ldo >= h * w && ldo % 32 == 0, PN_ERR_BAD_ARG, "mask_feature_resize: bad args");
+  dim3 grid(cdiv(ldo, 256), B * D);
+  mask_feature_resize_kernel<<<grid, 256, 0, st>>>(F, out, H, W, h, w, ldo, (float)H / (float)h,
+                                                   (float)W / (float)w);
+  return check_launch("mask_feature_resize_kernel");
+}
+
+// dst[b,r,:] = src[b, idx[b,r], :]  (row length L floats); grid.x = B*R rows, grid.y = chunks
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src,
+                                                           const int64_t* __restrict__ idx,
+                                                           float* __restrict__ dst, int Nsrc, int R, long long L,
+                                                           int vec) {
+  const int br = blockIdx.x;
+  const int b = br / R;
+  long long row = idx[br];
+  row = row < 0 ? 0 : (row >= Nsrc ? Nsrc - 1 : row);
+  const float* s = src + ((size_t)b * Nsrc + row) * L;
+  float* d = dst + (size_t)br * L;
+  if (vec) {
+    const long long n4 = L / 4;
+    for (long long i = (long long)blockIdx.y * 256 + threadIdx.x; i < n4; i += (long long)gridDim.y * 256)
+      reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
+  } else {
+    for (long long i = (long long)blockIdx.y * 256 + threadIdx.x; i < L; i += (long long)gridDim.y * 256)
+      d[i] = __ldg(s + i);
+  }
+}
+int launch_gather_rows(const float* src, const int64_t* idx, float* dst, int B, int Nsrc, int R, long long L,
+                       cudaStream_t st) {
+  PN_REQUIRE(src && idx && dst && B > 0 && R > 0 && L > 0, PN_ERR_BAD_ARG, "gather_rows: bad args");
+  const int vec = (L % 4 == 0) && (((uintptr_t)src & 15) == 0) && (((uintptr_t)dst & 15) == 0);
+  int chunks = cdiv(vec ? L / 4 : L, 256 * 8);
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  dim3 grid(B * R, chunks);
+  gather_rows_kernel<<<grid, 256, 0, st>>>(src, idx, dst, Nsrc, R, L, vec);
+  return check_launch("gather_rows_kernel");
+}
+
+}  // namespace pn

@@ -1,0 +1,78 @@
+"""``PSGTr`` detector wrapper -- the only caller of the hot path (reference
+``pairnet/models/frameworks/psgtr.py:73-156``): backbone -> ``bbox_head``.  Same class name,
+constructor and method signatures; backbone/pixel decoder are device-side PyTorch plumbing, the
+head is the CUDA library."""
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .registry import DETECTORS, build_backbone, build_head, to_config
+
+
+@DETECTORS.register_module()
+class PSGTr(nn.Module):
+    def __init__(self, backbone, bbox_head, train_cfg=None, test_cfg=None, pretrained=None, init_cfg=None, neck=None):
+        super().__init__()
+        if neck is not None:
+            raise NotImplementedError("PSGTr configs of Pair-Net have no neck")
+        self.backbone = build_backbone(to_config(backbone))
+        bbox_head = to_config(bbox_head)
+        bbox_head.update(train_cfg=train_cfg, test_cfg=test_cfg)  # mmdet SingleStageDetector.__init__
+        self.bbox_head = build_head(bbox_head)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.num_classes = self.bbox_head.num_classes
+
+    def init_weights(self):
+        self.backbone.init_weights()
+        self.bbox_head.init_weights()
+
+    def extract_feat(self, img):
+        return self.backbone(img)
+
+    def forward_dummy(self, img):
+        """psgtr.py:92-110."""
+        batch_size, _, height, width = img.shape
+        dummy_img_metas = [dict(batch_input_shape=(height, width), img_shape=(height, width, 3))
+                           for _ in range(batch_size)]
+        x = self.extract_feat(img)
+        return self.bbox_head(x, dummy_img_metas)
+
+    def forward_train(self, img, img_metas, gt_rels=None, gt_bboxes=None, gt_labels=None, gt_masks=None,
+                      gt_bboxes_ignore=None):
+        raise NotImplementedError("training (psgtr.py:112-146) depends on SURVEY §8f rank 2 (targets + losses)")
+
+    def simple_test(self, img, img_metas, rescale=False):
+        feat = self.extract_feat(img)
+        return self.bbox_head.simple_test(feat, img_metas, rescale=rescale)
+
+    def forward(self, img, img_metas=None, return_loss=False, **kwargs):
+        if return_loss:
+            return self.forward_train(img, img_metas, **kwargs)
+        return self.forward_dummy(img)
+
+
+class GraphedForward:
+    """Capture ``model.forward_dummy`` on a static input into one CUDA graph and replay it.
+
+    The whole query -> pair -> relation forward (plus the PyTorch upstream) then costs a single graph
+    launch per step; outputs are the static tensors of the captured run."""
+
+    def __init__(self, fn, example, warmup=3):
+        self.static_in = example.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):
+                fn(self.static_in)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = fn(self.static_in)
+
+    def __call__(self, x=None):
+        if x is not None and x.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

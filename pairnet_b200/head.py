@@ -1,0 +1,299 @@
+"""``CrossHead2`` -- the Pair-Net relation head, B200-native.
+
+Same constructor kwargs, parameter names, ``forward(feats, img_metas)`` contract and output dicts as the
+reference head (``pairnet/models/relation_heads/pairnet_head.py:22-417``), but the forward
+is ONE call into ``libpairnet_b200.so`` (``pn_head_forward``): Mask2Former masked-attention decoder ->
+Pair Proposal Network (sub/obj MLP, L2 norm, N x N pair matrix, ConvTiny, top-k, pair gather) ->
+Relation Fusion decoder -> output gathers.  There is no PyTorch/CPU fallback for that path.
+"""
+import copy
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+from .registry import (HEADS, ConfigDict, build_loss, build_plugin_layer, build_positional_encoding,
+                       build_transformer_layer_sequence, to_config)
+
+
+class ConvTiny(nn.Module):
+    """Weights of the Matrix-Learner filter (reference ``cnn_factory.py:6-53``; names
+    ``conv_layers.{0,1,2}.0``).  Evaluated by ``pn_conv_tiny``."""
+
+    def __init__(self, in_channels=1, out_channels=1, kernel_size=7, mid_channels=64, layers=3):
+        super().__init__()
+        if (in_channels, out_channels, kernel_size, layers) != (1, 1, 7, 3):
+            raise NotImplementedError("only the shipped ConvTiny geometry (1->mid->mid->1, k=7) is supported")
+        self.mid_channels = mid_channels
+        self.conv_layers = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(1, mid_channels, 7, padding=3), nn.ReLU(inplace=True)),
+            nn.Sequential(nn.Conv2d(mid_channels, mid_channels, 7, padding=3), nn.ReLU(inplace=True)),
+            nn.Sequential(nn.Conv2d(mid_channels, 1, 7, padding=3)),
+        ])
+
+    def forward(self, x):
+        from . import ops
+        return ops.conv_tiny(x, self)
+
+
+def creat_cnn(name):
+    """reference ``cnn_factory.creat_cnn`` (sic)."""
+    if name == "conv_tiny":
+        return ConvTiny()
+    raise NotImplementedError(f"mapper '{name}': only 'conv_tiny' is used by the shipped Pair-Net configs "
+                              "(conv_small hard-codes N=100, conv_base is a U-Net ablation)")
+
+
+def _mlp3(d):
+    return nn.Sequential(nn.Linear(d, d), nn.ReLU(inplace=True), nn.Linear(d, d), nn.ReLU(inplace=True), nn.Linear(d, d))
+
+
+def _ptr(t):
+    return t.data_ptr()
+
+
+@HEADS.register_module()
+class CrossHead2(nn.Module):
+    def __init__(self, num_classes, in_channels, num_relations, num_obj_query=100, num_rel_query=100,
+                 mapper="conv_tiny", use_mask=True, pixel_decoder=None, transformer_decoder=None, feat_channels=256,
+                 out_channels=256, num_transformer_feat_level=3, embed_dims=256, relation_decoder=None,
+                 enforce_decoder_input_project=False, n_heads=8,
+                 positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True),
+                 rel_cls_loss=None, subobj_cls_loss=None, importance_match_loss=None, loss_cls=None, loss_mask=None,
+                 loss_dice=None, train_cfg=None, test_cfg=dict(max_per_img=100), init_cfg=None, **kwargs):
+        super().__init__()
+        transformer_decoder = to_config(transformer_decoder)
+        relation_decoder = to_config(relation_decoder)
+        pixel_decoder = to_config(pixel_decoder)
+        positional_encoding = to_config(positional_encoding)
+        if embed_dims != nat.EMBED_DIMS or feat_channels != nat.EMBED_DIMS or out_channels != nat.EMBED_DIMS:
+            raise NotImplementedError("the CUDA library is compiled for embed_dims = feat_channels = out_channels = 256")
+        if enforce_decoder_input_project:
+            raise NotImplementedError("enforce_decoder_input_project=True is not used by the Pair-Net configs")
+        self.num_classes = num_classes
+        self.num_rel_query = num_rel_query
+        self.num_relations = num_relations
+        self.use_mask = use_mask
+        # construction order follows the reference (pairnet_head.py:62-176)
+        self.relation_decoder = build_transformer_layer_sequence(relation_decoder)
+        self.rel_query_embed = nn.Embedding(num_rel_query, feat_channels)
+        self.rel_query_embed2 = nn.Embedding(num_rel_query * 2, feat_channels)
+        self.rel_query_embed3 = nn.Embedding(num_rel_query * 2, feat_channels)  # dead in the reference forward
+        self.rel_query_feat = nn.Embedding(num_rel_query, feat_channels)
+        self.update_importance = creat_cnn(mapper)
+        self.n_heads = n_heads
+        self.embed_dims = embed_dims
+        assert "num_feats" in positional_encoding
+        assert positional_encoding["num_feats"] * 2 == embed_dims, (
+            f"embed_dims should be exactly 2 times of num_feats. Found {embed_dims} and {positional_encoding['num_feats']}.")
+        self.num_queries = num_obj_query
+        self.num_transformer_feat_level = num_transformer_feat_level
+        self.num_heads = transformer_decoder.transformerlayers.attn_cfgs.num_heads
+        if self.num_heads != 8 or n_heads != 8:
+            raise NotImplementedError("the CUDA library is compiled for 8 heads x 32")
+        self.with_pixel_decoder = pixel_decoder is not None
+        if self.with_pixel_decoder:
+            assert pixel_decoder.encoder.transformerlayers.attn_cfgs.num_levels == num_transformer_feat_level
+            pd = copy.deepcopy(pixel_decoder)
+            pd.update(in_channels=in_channels, feat_channels=feat_channels, out_channels=out_channels)
+            self.pixel_decoder = build_plugin_layer(pd)[1]
+        self.transformer_decoder = build_transformer_layer_sequence(transformer_decoder)
+        self.decoder_embed_dims = self.transformer_decoder.embed_dims
+        assert self.decoder_embed_dims == feat_channels
+        self.decoder_input_projs = nn.ModuleList([nn.Identity() for _ in range(num_transformer_feat_level)])
+        self.decoder_positional_encoding = build_positional_encoding(positional_encoding)
+        self.query_embed = nn.Embedding(num_obj_query, feat_channels)
+        self.query_feat = nn.Embedding(num_obj_query, feat_channels)
+        self.level_embed = nn.Embedding(num_transformer_feat_level, feat_channels)
+        self.cls_embed = nn.Linear(feat_channels, num_classes + 1)
+        self.mask_embed = _mlp3(feat_channels)
+        self.test_cfg = test_cfg
+        self.train_cfg = train_cfg
+        self.num_obj_query = num_obj_query
+        self.in_channels = in_channels
+        self.loss_cfgs = dict(loss_cls=loss_cls, loss_mask=loss_mask, loss_dice=loss_dice, rel_cls_loss=rel_cls_loss,
+                              subobj_cls_loss=subobj_cls_loss, importance_match_loss=importance_match_loss)
+        for name, cfg in self.loss_cfgs.items():
+            setattr(self, name, build_loss(cfg) if cfg is not None else None)
+        self.class_weight = loss_cls.get("class_weight") if loss_cls else None
+        self.cls_out_channels = num_classes if (loss_cls and loss_cls.get("use_sigmoid")) else num_classes + 1
+        self.sub_query_update = _mlp3(embed_dims)
+        self.obj_query_update = _mlp3(embed_dims)
+        self.rel_cls_embed = nn.Linear(embed_dims, num_relations)
+        # native-side caches
+        self._wkey = None
+        self._wstruct = None
+        self._pos_cache = {}
+        self._ws = None
+
+    # ------------------------------------------------------------------ reference API
+    def init_weights(self):
+        """pairnet_head.py:178-193."""
+        if self.with_pixel_decoder:
+            self.pixel_decoder.init_weights()
+        for p in self.transformer_decoder.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_normal_(p)
+        for p in self.relation_decoder.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_normal_(p)
+
+    def forward(self, feats, img_metas=None):
+        """feats: 4 backbone maps [B,C_i,H_i,W_i] -> (all_cls_scores, all_mask_preds)  (pairnet_head.py:260-417)."""
+        mask_features, memorys = self.pixel_decoder(feats)
+        return self.forward_from_memories(mask_features, memorys)
+
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError("training targets/losses (pairnet_head.py:419-757) are SURVEY §8f rank 2, not built yet")
+
+    def simple_test_bboxes(self, feats, img_metas, rescale=False):
+        raise NotImplementedError("post-processing (pairnet_head.py:759-924) is SURVEY §8f rank 3, not built yet")
+
+    simple_test = simple_test_bboxes
+
+    # ------------------------------------------------------------------ native plumbing
+    def _hot_params(self):
+        ps = [self.query_feat.weight, self.query_embed.weight, self.level_embed.weight, self.cls_embed.weight,
+              self.rel_query_feat.weight, self.rel_query_embed.weight, self.rel_query_embed2.weight]
+        for m in (self.transformer_decoder, self.relation_decoder, self.mask_embed, self.sub_query_update,
+                  self.obj_query_update, self.update_importance, self.rel_cls_embed, self.cls_embed):
+            ps.extend(m.parameters())
+        return ps
+
+    @staticmethod
+    def _lin(dst, mod):
+        dst.w = _ptr(mod.weight)
+        dst.b = _ptr(mod.bias) if mod.bias is not None else None
+
+    @staticmethod
+    def _norm(dst, mod):
+        dst.gamma, dst.beta = _ptr(mod.weight), _ptr(mod.bias)
+
+    def _mlp(self, dst, seq):
+        for i, j in enumerate((0, 2, 4)):
+            self._lin(dst.l[i], seq[j])
+
+    def _layer(self, dst, layer):
+        for d, a in ((dst.cross_attn, layer.attentions[0].attn), (dst.self_attn, layer.attentions[1].attn)):
+            d.in_proj_w, d.in_proj_b = _ptr(a.in_proj_weight), _ptr(a.in_proj_bias)
+            d.out_proj_w, d.out_proj_b = _ptr(a.out_proj.weight), _ptr(a.out_proj.bias)
+        self._lin(dst.ffn1, layer.ffns[0].layers[0][0])
+        self._lin(dst.ffn2, layer.ffns[0].layers[1])
+        for i in range(3):
+            self._norm(dst.norm[i], layer.norms[i])
+
+    def native_weights(self):
+        """``PnHeadWeights`` over the current parameter storage (rebuilt when any pointer changes)."""
+        params = self._hot_params()
+        key = tuple(p.data_ptr() for p in params)
+        if key == self._wkey:
+            return self._wstruct
+        for p in params:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise nat.NativeError("CrossHead2 hot-path parameters must be contiguous fp32 CUDA tensors "
+                                      "(move the head to a B200 with .cuda(); there is no CPU path)")
+        w = nat.PnHeadWeights()
+        m = w.m2f
+        td = self.transformer_decoder
+        m.num_queries, m.num_layers, m.num_levels = self.num_queries, len(td.layers), self.num_transformer_feat_level
+        m.ffn_dims, m.num_cls = td.layers[0].ffns[0].feedforward_channels, self.num_classes + 1
+        if len(td.layers) > nat.PN_MAX_LAYERS or len(self.relation_decoder.layers) > nat.PN_MAX_LAYERS:
+            raise NotImplementedError("too many decoder layers for PN_MAX_LAYERS")
+        m.query_feat, m.query_embed, m.level_embed = _ptr(self.query_feat.weight), _ptr(self.query_embed.weight), _ptr(self.level_embed.weight)
+        self._norm(m.post_norm, td.post_norm)
+        self._lin(m.cls_embed, self.cls_embed)
+        self._mlp(m.mask_embed, self.mask_embed)
+        for i, layer in enumerate(td.layers):
+            self._layer(m.layers[i], layer)
+        self._mlp(w.sub_query_update, self.sub_query_update)
+        self._mlp(w.obj_query_update, self.obj_query_update)
+        cv = w.update_importance
+        cv.mid_channels = self.update_importance.mid_channels
+        for i in range(3):
+            conv = self.update_importance.conv_layers[i][0]
+            cv.w[i], cv.b[i] = _ptr(conv.weight), _ptr(conv.bias)
+        r = w.rel
+        rd = self.relation_decoder
+        r.num_rel_queries, r.num_layers = self.num_rel_query, len(rd.layers)
+        r.ffn_dims, r.num_rel_cls = rd.layers[0].ffns[0].feedforward_channels, self.num_relations
+        r.rel_query_feat, r.rel_query_embed = _ptr(self.rel_query_feat.weight), _ptr(self.rel_query_embed.weight)
+        r.rel_query_embed2 = _ptr(self.rel_query_embed2.weight)
+        self._lin(r.rel_cls_embed, self.rel_cls_embed)
+        for i, layer in enumerate(rd.layers):
+            self._layer(r.layers[i], layer)
+        self._wkey, self._wstruct = key, w
+        return w
+
+    def _pos_table(self, h, w, device, stream):
+        key = (h, w, str(device))
+        if key not in self._pos_cache:
+            t = torch.empty((h * w, nat.EMBED_DIMS), dtype=torch.float32, device=device)
+            nat.check(nat.load().pn_sine_posenc(t.data_ptr(), h, w, stream), "pn_sine_posenc")
+            self._pos_cache[key] = t
+        return self._pos_cache[key]
+
+    @torch.no_grad()
+    def forward_from_memories(self, mask_features, memorys, taps=None, materialize_seg=True):
+        """The hot path proper: everything in ``CrossHead2.forward`` after the pixel decoder.
+
+        taps: optional dict; when given, per-stage intermediates are written into it (parity tests)."""
+        lib = nat.load()
+        dev = mask_features.device
+        if dev.type != "cuda":
+            raise nat.NativeError("CrossHead2.forward needs CUDA tensors on a B200; there is no CPU fallback")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        mask_features = mask_features.float().contiguous()
+        memorys = [m.float().contiguous() for m in memorys]
+        B, Cc, H4, W4 = mask_features.shape
+        assert Cc == nat.EMBED_DIMS and len(memorys) == self.num_transformer_feat_level
+        N, R, K = self.num_queries, self.num_rel_query, self.num_rel_query
+        ncls, nrel = self.num_classes + 1, self.num_relations
+        w = self.native_weights()
+        inp = nat.PnM2FInputs()
+        inp.B, inp.H4, inp.W4, inp.mask_features = B, H4, W4, mask_features.data_ptr()
+        keep = []
+        for l, m in enumerate(memorys):
+            inp.h[l], inp.w[l], inp.memory[l] = m.shape[2], m.shape[3], m.data_ptr()
+            pt = self._pos_table(m.shape[2], m.shape[3], dev, stream)
+            inp.pos[l] = pt.data_ptr()
+            keep.append(pt)
+        f32 = dict(dtype=torch.float32, device=dev)
+        o = dict(cls=torch.empty((B, N, ncls), **f32), mask=torch.empty((B, N, H4, W4), **f32),
+                 importance=torch.empty((B, N, N), **f32), rel=torch.empty((B, R, nrel), **f32),
+                 sub_pos=torch.empty((B, K), dtype=torch.int64, device=dev),
+                 obj_pos=torch.empty((B, K), dtype=torch.int64, device=dev),
+                 sub=torch.empty((B, K, ncls), **f32), obj=torch.empty((B, K, ncls), **f32))
+        if materialize_seg:
+            o["sub_seg"] = torch.empty((B, K, H4, W4), **f32)
+            o["obj_seg"] = torch.empty((B, K, H4, W4), **f32)
+        out = nat.PnHeadOutputs()
+        for k, t in o.items():
+            setattr(out, k, t.data_ptr())
+        if taps is not None:
+            nl = len(self.transformer_decoder.layers)
+            words = max((m.shape[2] * m.shape[3] + 63) // 64 * 2 for m in memorys)
+            t = dict(query_out=torch.empty((B, N, 256), **f32), importance_raw=torch.empty((B, N, N), **f32),
+                     pair_feat=torch.empty((B, 2 * K, 256), **f32), rel_feat=torch.empty((B, R, 256), **f32),
+                     query_trace=torch.empty((nl, B, N, 256), **f32),
+                     mask_trace=torch.zeros((nl, B, N, words), dtype=torch.int32, device=dev))
+            for k, v in t.items():
+                setattr(out, k, v.data_ptr())
+            out.trace_words = words
+            taps.update(t)
+        need = lib.pn_head_workspace_bytes(C.byref(w), C.byref(inp))
+        if need == 0:
+            raise nat.NativeError("pn_head_workspace_bytes: " + lib.pn_last_error_string().decode())
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        nat.check(lib.pn_head_forward(C.byref(w), C.byref(inp), C.byref(out), self._ws.data_ptr(), self._ws.numel(),
+                                      stream), "pn_head_forward")
+        self.last_launch_count = lib.pn_last_launch_count()
+        all_cls_scores = dict(sub=o["sub"], obj=o["obj"], cls=o["cls"], rel=o["rel"], importance=o["importance"])
+        all_mask_preds = dict(mask=o["mask"])
+        if materialize_seg:
+            all_mask_preds.update(sub_seg=o["sub_seg"], obj_seg=o["obj_seg"])
+        if taps is not None:
+            taps.update(sub_pos=o["sub_pos"], obj_pos=o["obj_pos"])
+        self.last_pairs = (o["sub_pos"], o["obj_pos"])
+        return all_cls_scores, all_mask_preds

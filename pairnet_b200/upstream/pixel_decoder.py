@@ -1,0 +1,205 @@
+"""UPSTREAM of the hot path ("next"): mmdet 2.25.1 ``MSDeformAttnPixelDecoder``
+(cfg ``configs/mask2former/pairnet.py:33-71``, call site ``pairnet_head.py:262``) as device-side
+PyTorch plumbing (cuDNN / cuBLAS / ``grid_sample``), batch-first.  It produces ``mask_features`` and
+the three memories the CUDA hot path consumes.  Parameter names follow mmdet so checkpoints load.
+Not hand-written CUDA yet -- listed as the next row to take over."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..registry import PLUGIN_LAYERS
+
+
+def sine_pos_2d(h, w, num_feats=128, temperature=10000.0, scale=2 * math.pi, eps=1e-6, device=None,
+                dtype=torch.float32):
+    """[2*num_feats, h, w] normalised sine encoding of an all-valid image (mmdet SinePositionalEncoding)."""
+    y = torch.arange(1, h + 1, dtype=dtype, device=device) / (h + eps) * scale
+    x = torch.arange(1, w + 1, dtype=dtype, device=device) / (w + eps) * scale
+    i = torch.arange(num_feats, dtype=dtype, device=device)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_feats)
+    px = x[:, None] / dim_t
+    py = y[:, None] / dim_t
+    px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)  # [w, F]
+    py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)  # [h, F]
+    pos = torch.cat((py[:, None, :].expand(h, w, num_feats), px[None, :, :].expand(h, w, num_feats)), dim=2)
+    return pos.permute(2, 0, 1).contiguous()
+
+
+class ConvModule(nn.Module):
+    """mmcv ConvModule subset: conv -> GroupNorm -> (ReLU)."""
+
+    def __init__(self, cin, cout, k, padding=0, bias=False, groups=32, act=False):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=bias)
+        self.gn = nn.GroupNorm(groups, cout)
+        self.with_act = act
+
+    def forward(self, x):
+        x = self.gn(self.conv(x))
+        return F.relu(x, inplace=True) if self.with_act else x
+
+
+class MultiScaleDeformableAttention(nn.Module):
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=3, num_points=4, **kwargs):
+        super().__init__()
+        self.embed_dims, self.num_heads, self.num_levels, self.num_points = embed_dims, num_heads, num_levels, num_points
+        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.init_weights()
+
+    def init_weights(self):
+        nn.init.zeros_(self.sampling_offsets.weight)
+        th = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        g = torch.stack([th.cos(), th.sin()], -1)
+        g = (g / g.abs().max(-1, keepdim=True)[0]).view(self.num_heads, 1, 1, 2).repeat(1, self.num_levels, self.num_points, 1)
+        for i in range(self.num_points):
+            g[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(g.reshape(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.zeros_(self.value_proj.bias)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.zeros_(self.output_proj.bias)
+
+    def forward(self, x, pos, ref, shapes, normalizer):
+        """x,pos [B,nq,C]; ref [1,nq,1,L,1,2]; normalizer [1,1,1,L,1,2]; returns x + attn(x)."""
+        B, nq, C = x.shape
+        H, L, Pn = self.num_heads, self.num_levels, self.num_points
+        q = x + pos
+        value = self.value_proj(x).view(B, nq, H, C // H)
+        offs = self.sampling_offsets(q).view(B, nq, H, L, Pn, 2)
+        attw = self.attention_weights(q).view(B, nq, H, L * Pn).softmax(-1).view(B, nq, H, L, Pn)
+        grids = 2 * (ref + offs / normalizer) - 1  # [B,nq,H,L,P,2]
+        out = None
+        start = 0
+        for lvl, (h, w) in enumerate(shapes):
+            v = value[:, start:start + h * w].permute(0, 2, 3, 1).reshape(B * H, C // H, h, w)
+            start += h * w
+            g = grids[:, :, :, lvl].permute(0, 2, 1, 3, 4).reshape(B * H, nq, Pn, 2)
+            s = F.grid_sample(v, g, mode="bilinear", padding_mode="zeros", align_corners=False)  # [B*H,c,nq,P]
+            wl = attw[:, :, :, lvl].permute(0, 2, 1, 3).reshape(B * H, 1, nq, Pn)
+            c = (s * wl).sum(-1)
+            out = c if out is None else out + c
+        out = out.view(B, C, nq).transpose(1, 2)
+        return x + self.output_proj(out)
+
+
+class _FFN(nn.Module):
+    def __init__(self, d, ff):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Sequential(nn.Linear(d, ff), nn.ReLU(inplace=True), nn.Dropout(0.0)),
+                                    nn.Linear(ff, d), nn.Dropout(0.0))
+
+    def forward(self, x):
+        return x + self.layers(x)
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, d, ff, attn_cfg):
+        super().__init__()
+        self.attentions = nn.ModuleList([MultiScaleDeformableAttention(**attn_cfg)])
+        self.ffns = nn.ModuleList([_FFN(d, ff)])
+        self.norms = nn.ModuleList([nn.LayerNorm(d), nn.LayerNorm(d)])
+
+    def forward(self, x, pos, ref, shapes, normalizer):
+        x = self.norms[0](self.attentions[0](x, pos, ref, shapes, normalizer))
+        return self.norms[1](self.ffns[0](x))
+
+
+class _Encoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        tl = cfg["transformerlayers"]
+        if tuple(tl["operation_order"]) != ("self_attn", "norm", "ffn", "norm"):
+            raise NotImplementedError("pixel-decoder encoder order")
+        attn = {k: v for k, v in dict(tl["attn_cfgs"]).items() if k in ("embed_dims", "num_heads", "num_levels", "num_points")}
+        d = attn.get("embed_dims", 256)
+        ff = tl["ffn_cfgs"].get("feedforward_channels", 1024)
+        self.layers = nn.ModuleList([_EncoderLayer(d, ff, attn) for _ in range(cfg["num_layers"])])
+        self.num_levels = attn.get("num_levels", 3)
+
+
+@PLUGIN_LAYERS.register_module()
+class MSDeformAttnPixelDecoder(nn.Module):
+    def __init__(self, in_channels=(256, 512, 1024, 2048), strides=(4, 8, 16, 32), feat_channels=256,
+                 out_channels=256, num_outs=3, norm_cfg=None, act_cfg=None, encoder=None, positional_encoding=None,
+                 init_cfg=None):
+        super().__init__()
+        self.strides = list(strides)
+        self.num_input_levels = len(in_channels)
+        self.encoder = _Encoder(encoder)
+        self.num_encoder_levels = self.encoder.num_levels
+        groups = (norm_cfg or {}).get("num_groups", 32)
+        self.input_convs = nn.ModuleList([
+            ConvModule(in_channels[i], feat_channels, 1, bias=True, groups=groups)
+            for i in range(self.num_input_levels - 1, self.num_input_levels - self.num_encoder_levels - 1, -1)])
+        self.postional_encoding = nn.Identity()  # parameter-free; name kept from mmdet
+        self.num_pos_feats = (positional_encoding or {}).get("num_feats", feat_channels // 2)
+        self.level_encoding = nn.Embedding(self.num_encoder_levels, feat_channels)
+        self.lateral_convs = nn.ModuleList()
+        self.output_convs = nn.ModuleList()
+        for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
+            self.lateral_convs.append(ConvModule(in_channels[i], feat_channels, 1, bias=False, groups=groups))
+            self.output_convs.append(ConvModule(feat_channels, feat_channels, 3, padding=1, bias=False, groups=groups, act=True))
+        self.mask_feature = nn.Conv2d(feat_channels, out_channels, 1)
+        self.num_outs = num_outs
+        self._static = {}
+
+    def init_weights(self):
+        for m in list(self.input_convs) + list(self.lateral_convs) + list(self.output_convs):
+            nn.init.xavier_uniform_(m.conv.weight)
+            if m.conv.bias is not None:
+                nn.init.zeros_(m.conv.bias)
+        nn.init.kaiming_uniform_(self.mask_feature.weight, a=1)
+        nn.init.zeros_(self.mask_feature.bias)
+        nn.init.normal_(self.level_encoding.weight, 0, 1)
+        for p in self.encoder.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_normal_(p)
+        for layer in self.encoder.layers:
+            layer.attentions[0].init_weights()
+
+    def _geometry(self, shapes, device, dtype):
+        key = (tuple(shapes), str(device), dtype)
+        if key not in self._static:
+            pos, ref = [], []
+            for i, (h, w) in enumerate(shapes):
+                p = sine_pos_2d(h, w, self.num_pos_feats, device=device, dtype=dtype)
+                pos.append((i, p.flatten(1).t()))
+                ys = (torch.arange(h, dtype=dtype, device=device) + 0.5) / h
+                xs = (torch.arange(w, dtype=dtype, device=device) + 0.5) / w
+                yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+                ref.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+            refp = torch.cat(ref, 0)[None, :, None, None, None, :]
+            norm = torch.tensor([[w, h] for h, w in shapes], dtype=dtype, device=device)[None, None, None, :, None, :]
+            self._static[key] = (pos, refp, norm)
+        return self._static[key]
+
+    def forward(self, feats):
+        B = feats[0].shape[0]
+        shapes, xs = [], []
+        for i in range(self.num_encoder_levels):
+            f = feats[self.num_input_levels - i - 1]
+            shapes.append(tuple(f.shape[-2:]))
+            xs.append(self.input_convs[i](f).flatten(2).transpose(1, 2))
+        pos_l, ref, norm = self._geometry(shapes, feats[0].device, feats[0].dtype)
+        pos = torch.cat([p + self.level_encoding.weight[i][None, :] for i, p in pos_l], 0)[None]
+        x = torch.cat(xs, 1)
+        for layer in self.encoder.layers:
+            x = layer(x, pos, ref, shapes, norm)
+        mem = x.transpose(1, 2)
+        outs, start = [], 0
+        for h, w in shapes:
+            outs.append(mem[:, :, start:start + h * w].reshape(B, -1, h, w))
+            start += h * w
+        for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
+            cur = self.lateral_convs[i](feats[i])
+            y = cur + F.interpolate(outs[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
+            outs.append(self.output_convs[i](y))
+        return self.mask_feature(outs[-1]), outs[: self.num_outs]

@@ -1,0 +1,197 @@
+"""GPU (-m gpu): the whole hot path (pn_head_forward through CrossHead2) against the CPU oracle, the
+committed golden fixtures, and size-independent properties at BASELINE.json's full size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import (GOLDEN, RTOL_LOGITS, check_topk_tie_aware, oracle_small_head, product_small_head, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def heads():
+    o = oracle_small_head()
+    return o, product_small_head(o)
+
+
+def _run_product(head, mf, mems, taps=None):
+    cls, msk = head.forward_from_memories(mf.cuda(), [m.cuda() for m in mems], taps=taps)
+    torch.cuda.synchronize()
+    return cls, msk
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_head_matches_oracle_and_golden(heads, case):
+    from oracle.make_golden import HEAD_CASES, small_head_inputs
+    from pairnet_b200 import ops
+    o, p = heads
+    tag, B, hw4, seed = HEAD_CASES[case]
+    mf, mems = small_head_inputs(B, hw4, seed)
+    tr = {}
+    with torch.no_grad():
+        ocls, omsk = o.forward_from_memories(mf, mems, trace=tr)
+    taps = {}
+    cls, msk = _run_product(p, mf, mems, taps)
+
+    # --- per-layer: attention masks (bits) and query features
+    for i, am in enumerate(tr["attn_mask"]):
+        hw = am.shape[-1]
+        got = ops.unpack_bits(taps["mask_trace"][i], hw).cpu()
+        frac = float((got != am).float().mean())
+        assert frac < 2e-4, f"layer {i}: {frac} of attention-mask bits differ"
+        q_ref = tr["query_feat"][i].transpose(0, 1)
+        assert rel_err(taps["query_trace"][i], q_ref) < RTOL_LOGITS, f"layer {i} query_feat"
+    # --- PPN
+    assert rel_err(taps["importance_raw"], tr["importance_raw"]) < RTOL_LOGITS
+    assert rel_err(cls["importance"], ocls["importance"]) < RTOL_LOGITS
+    tol = RTOL_LOGITS * float(ocls["importance"].abs().max())
+    swapped = check_topk_tie_aware(ocls["importance"], taps["sub_pos"], taps["obj_pos"], tr["sub_pos"], tr["obj_pos"], tol)
+    assert swapped <= 4
+    # --- relation fusion + logits (north_star: 1e-3 relative on fp32 logits)
+    if swapped == 0:
+        assert rel_err(taps["pair_feat"], tr["pair_feat"].transpose(0, 1)) < RTOL_LOGITS
+        assert rel_err(taps["rel_feat"], tr["rel_feat"][-1].transpose(0, 1)) < RTOL_LOGITS
+        assert rel_err(cls["rel"], ocls["rel"]) < RTOL_LOGITS
+        assert rel_err(cls["sub"], ocls["sub"]) < RTOL_LOGITS
+        assert rel_err(cls["obj"], ocls["obj"]) < RTOL_LOGITS
+        assert rel_err(msk["sub_seg"], omsk["sub_seg"]) < RTOL_LOGITS
+    assert rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
+    assert rel_err(msk["mask"], omsk["mask"]) < RTOL_LOGITS
+    # --- committed golden fixture (minted by oracle/make_golden.py)
+    g = np.load(os.path.join(GOLDEN, f"head_small_{tag}.npz"))
+    assert rel_err(cls["cls"], g["cls"]) < RTOL_LOGITS
+    assert rel_err(cls["importance"], g["importance"]) < RTOL_LOGITS
+    assert rel_err(msk["mask"][:, :, ::4, ::4], g["mask_sub4"]) < RTOL_LOGITS
+    assert rel_err(taps["query_out"], np.transpose(g["query_last"], (1, 0, 2))) < RTOL_LOGITS
+    if swapped == 0:
+        assert np.array_equal(taps["sub_pos"].cpu().numpy(), g["sub_pos"])
+        assert np.array_equal(taps["obj_pos"].cpu().numpy(), g["obj_pos"])
+        assert rel_err(cls["rel"], g["rel"]) < RTOL_LOGITS
+
+
+def test_stage_ppn_and_relation_fusion_from_oracle_inputs(heads):
+    """Feed the ORACLE's last-layer queries / pair features to the stage entry points."""
+    import ctypes as C
+    from oracle.make_golden import HEAD_CASES, small_head_inputs
+    from pairnet_b200 import _native as nat
+    o, p = heads
+    tag, B, hw4, seed = HEAD_CASES[0]
+    mf, mems = small_head_inputs(B, hw4, seed)
+    tr = {}
+    with torch.no_grad():
+        ocls, _ = o.forward_from_memories(mf, mems, trace=tr)
+    lib = nat.load()
+    w = p.native_weights()
+    N, K, dev = 100, 100, "cuda"
+    q = tr["query_feat"][-1].transpose(0, 1).contiguous().cuda()
+    need = lib.pn_ppn_workspace_bytes(B, N, K, 64)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    raw = torch.empty((B, N, N), device=dev)
+    imp = torch.empty((B, N, N), device=dev)
+    sp = torch.empty((B, K), dtype=torch.int64, device=dev)
+    op = torch.empty((B, K), dtype=torch.int64, device=dev)
+    pair = torch.empty((B, 2 * K, 256), device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    nat.check(lib.pn_ppn_forward(q.data_ptr(), None, C.byref(w.sub_query_update), C.byref(w.obj_query_update),
+                                 C.byref(w.update_importance), raw.data_ptr(), imp.data_ptr(), None, sp.data_ptr(),
+                                 op.data_ptr(), pair.data_ptr(), B, N, K, ws.data_ptr(), need, st), "ppn")
+    assert rel_err(raw, tr["importance_raw"]) < 1e-5
+    assert rel_err(imp, ocls["importance"]) < 1e-5
+    tol = 1e-5 * float(ocls["importance"].abs().max())
+    swapped = check_topk_tie_aware(ocls["importance"], sp, op, tr["sub_pos"], tr["obj_pos"], tol)
+    assert swapped == 0
+    assert torch.equal(pair.cpu(), tr["pair_feat"].transpose(0, 1))  # pure gather: bit-exact
+
+    need = lib.pn_relation_fusion_workspace_bytes(B, 100, 200, 2048)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    rel = torch.empty((B, 100, 56), device=dev)
+    pf = tr["pair_feat"].transpose(0, 1).contiguous().cuda()
+    nat.check(lib.pn_relation_fusion_forward(C.byref(w.rel), pf.data_ptr(), rel.data_ptr(), None, B, 200,
+                                             ws.data_ptr(), need, st), "rel")
+    assert rel_err(rel, ocls["rel"]) < 2e-5
+
+
+def _full_size_inputs(B, seed):
+    from oracle.weights import numpy_tensor
+    mf = numpy_tensor((B, 256, 200, 334), seed, 0.5)
+    mems = [numpy_tensor((B, 256, 25, 42), seed + 1), numpy_tensor((B, 256, 50, 84), seed + 2),
+            numpy_tensor((B, 256, 100, 167), seed + 3)]
+    return mf, mems
+
+
+def test_full_size_properties(heads):
+    """BASELINE config 2 size (bs=2, 800x1333 -> 200x334 / 25x42 / 50x84 / 100x167): properties that do
+    not need the CPU oracle at this size."""
+    _, p = heads
+    mf, mems = _full_size_inputs(2, 31)
+    taps = {}
+    cls, msk = _run_product(p, mf, mems, taps)
+    sp, op = taps["sub_pos"], taps["obj_pos"]
+    # determinism: second run is bit-identical
+    cls2, msk2 = _run_product(p, mf, mems)
+    for k in cls:
+        assert torch.equal(cls[k], cls2[k]), k
+    assert torch.equal(msk["mask"], msk2["mask"])
+    # batch permutation equivariance (per-image independence, no cross-image op): bit-exact
+    cls3, msk3 = _run_product(p, mf.flip(0), [m.flip(0) for m in mems])
+    for k in cls:
+        assert torch.equal(cls[k], cls3[k].flip(0)), k
+    # top-k: sorted descending, and nothing outside the selection beats the k-th value
+    imp = cls["importance"].flatten(1)
+    flat = sp * 100 + op
+    vals = torch.gather(imp, 1, flat)
+    assert bool((vals[:, :-1] >= vals[:, 1:]).all())
+    rest = imp.clone()
+    rest.scatter_(1, flat, float("-inf"))
+    assert bool((rest.max(1).values <= vals[:, -1]).all())
+    assert all(len(set(r.tolist())) == 100 for r in flat.cpu())
+    # output gathers are pure index lookups: bit-exact (pairnet_head.py:380-403)
+    assert torch.equal(cls["sub"], torch.gather(cls["cls"], 1, sp[..., None].expand(-1, -1, 134)))
+    assert torch.equal(cls["obj"], torch.gather(cls["cls"], 1, op[..., None].expand(-1, -1, 134)))
+    for b in range(2):
+        assert torch.equal(msk["sub_seg"][b], msk["mask"][b][sp[b]])
+        assert torch.equal(msk["obj_seg"][b], msk["mask"][b][op[b]])
+    assert torch.equal(taps["pair_feat"][:, :100], torch.gather(taps["query_out"], 1, sp[..., None].expand(-1, -1, 256)))
+    # importance is ConvTiny(S O^T) with unit-norm rows: raw cosine matrix within [-1, 1]
+    assert float(taps["importance_raw"].abs().max()) <= 1.0 + 1e-5
+    assert all(torch.isfinite(v).all() for v in list(cls.values()) + list(msk.values()))
+
+
+def test_full_size_single_image_vs_oracle(heads):
+    """One 800x1333-sized image through the CPU oracle (a few seconds) vs the CUDA path."""
+    o, p = heads
+    mf, mems = _full_size_inputs(1, 41)
+    tr = {}
+    with torch.no_grad():
+        ocls, omsk = o.forward_from_memories(mf, mems, trace=tr)
+    taps = {}
+    cls, msk = _run_product(p, mf, mems, taps)
+    assert rel_err(taps["query_out"], tr["query_feat"][-1].transpose(0, 1)) < RTOL_LOGITS
+    assert rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
+    assert rel_err(msk["mask"], omsk["mask"]) < RTOL_LOGITS
+    assert rel_err(cls["importance"], ocls["importance"]) < RTOL_LOGITS
+    tol = RTOL_LOGITS * float(ocls["importance"].abs().max())
+    swapped = check_topk_tie_aware(ocls["importance"], taps["sub_pos"], taps["obj_pos"], tr["sub_pos"], tr["obj_pos"], tol)
+    if swapped == 0:
+        assert rel_err(cls["rel"], ocls["rel"]) < RTOL_LOGITS
+
+
+def test_detector_end_to_end_small_image():
+    """PSGTr(backbone + pixel decoder + head) built from the config on a small image: the drop-in call."""
+    from pairnet_b200.registry import Config, build_detector
+    from tests.util import ROOT
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_r50_b200.py"))
+    torch.manual_seed(10086)
+    model = build_detector(cfg.model)
+    model.init_weights()
+    model = model.cuda().eval()
+    img = torch.randn(2, 3, 256, 320, device="cuda")
+    with torch.no_grad():
+        cls, msk = model.forward_dummy(img)
+    assert cls["rel"].shape == (2, 100, 56) and cls["importance"].shape == (2, 100, 100)
+    assert msk["mask"].shape == (2, 100, 64, 80) and msk["sub_seg"].shape == (2, 100, 64, 80)
+    assert all(torch.isfinite(v).all() for v in cls.values())
+    assert model.bbox_head.last_launch_count > 100

@@ -1,0 +1,217 @@
+"""GPU (-m gpu): stage-wise parity of every C-ABI entry point against the CPU oracle / torch fp64 on the
+same seeded inputs.  Bit-exact for index/byte work, stated tolerance for fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(shape, seed, scale=1.0):
+    from oracle.weights import numpy_tensor
+    return numpy_tensor(shape, seed, scale)
+
+
+@pytest.mark.parametrize("h,w", [(4, 6), (13, 17), (25, 42), (50, 84)])
+def test_sine_posenc(h, w):
+    from oracle.bricks import sine_positional_encoding
+    from pairnet_b200 import ops
+    ref = sine_positional_encoding(torch.zeros(1, h, w, dtype=torch.bool))[0].flatten(1).t()
+    got = ops.sine_posenc(h, w).cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) < 5e-6  # sinf/cosf/powf ulp differences only
+
+
+def test_level_prep_bit_exact():
+    from pairnet_b200 import ops
+    B, h, w = 2, 9, 13
+    mem, lvl, pos = _t((B, 256, h, w), 1), _t((256,), 2), _t((h * w, 256), 3)
+    x, xp = ops.level_prep(mem.cuda(), lvl.cuda(), pos.cuda())
+    rx = mem.flatten(2).permute(0, 2, 1) + lvl.view(1, 1, -1)
+    assert torch.equal(x.cpu(), rx)
+    assert torch.equal(xp.cpu(), rx + pos[None])
+
+
+@pytest.mark.parametrize("H,W,h,w", [(32, 48, 4, 6), (40, 56, 20, 28), (50, 84, 13, 21), (200, 334, 25, 42)])
+def test_mask_feature_resize(H, W, h, w):
+    from pairnet_b200 import ops
+    Fm = _t((1, 256, H, W), 4)
+    ref = F.interpolate(Fm, (h, w), mode="bilinear", align_corners=False).flatten(2)
+    got = ops.mask_feature_resize(Fm.cuda(), h, w).cpu()
+    assert got.shape[2] % 64 == 0
+    assert float((got[:, :, : h * w] - ref).abs().max()) < 2e-6 * float(ref.abs().max()) + 1e-6
+    assert float(got[:, :, h * w:].abs().max()) == 0.0 if got.shape[2] > h * w else True
+
+
+@pytest.mark.parametrize("M,N,K,relu,resid", [(200, 256, 256, False, False), (200, 2048, 256, True, False),
+                                             (200, 256, 2048, False, True), (200, 134, 256, False, False),
+                                             (37, 56, 256, False, False), (2100, 256, 256, False, False),
+                                             (4099, 512, 256, True, True)])
+def test_linear(M, N, K, relu, resid):
+    from pairnet_b200 import ops
+    x, w, b = _t((M, K), 5), _t((N, K), 6, 0.1), _t((N,), 7)
+    r = _t((M, N), 8) if resid else None
+    ref = x.double() @ w.double().t() + b.double()
+    if relu:
+        ref = ref.relu()
+    if resid:
+        ref = ref + r.double()
+    got = ops.linear(x.cuda(), w.cuda(), b.cuda(), relu=relu, resid=r.cuda() if resid else None).cpu()
+    assert rel_err(got, ref) < 2e-6
+
+
+def test_add_layernorm():
+    from pairnet_b200 import ops
+    x, r, g, b = _t((203, 256), 9), _t((203, 256), 10), _t((256,), 11), _t((256,), 12)
+    ref = F.layer_norm((x + r).double(), (256,), g.double(), b.double(), 1e-5)
+    got = ops.add_layernorm(x.cuda(), r.cuda(), g.cuda(), b.cuda()).cpu()
+    assert rel_err(got, ref) < 2e-6
+
+
+def _mha_ref(q, k, v, blocked=None):
+    B, Nq, _ = q.shape
+    Nk = k.shape[1]
+    qh = q.double().view(B, Nq, 8, 32).transpose(1, 2) / np.sqrt(32.0)
+    kh = k.double().view(B, Nk, 8, 32).transpose(1, 2)
+    vh = v.double().view(B, Nk, 8, 32).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if blocked is not None:
+        blocked = blocked.clone()
+        blocked[blocked.all(-1)] = False  # pairnet_head.py:300
+        s = s.masked_fill(blocked[:, None], float("-inf"))
+    return (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Nq, 256)
+
+
+@pytest.mark.parametrize("Nq,Nk", [(100, 100), (100, 200), (100, 1050), (100, 4200), (130, 333)])
+def test_mha_core_unmasked(Nq, Nk):
+    from pairnet_b200 import ops
+    q, k, v = _t((2, Nq, 256), 13), _t((2, Nk, 256), 14), _t((2, Nk, 256), 15)
+    got = ops.mha_core(q.cuda(), k.cuda(), v.cuda()).cpu()
+    assert rel_err(got, _mha_ref(q, k, v)) < 5e-6
+
+
+@pytest.mark.parametrize("Nk", [70, 1050, 4200])
+def test_mha_core_masked_with_fully_blocked_rows(Nk):
+    from pairnet_b200 import ops
+    B, Nq = 2, 100
+    q, k, v = _t((B, Nq, 256), 16, 2.0), _t((B, Nk, 256), 17), _t((B, Nk, 256), 18)
+    rng = np.random.default_rng(Nk)
+    blocked = torch.from_numpy(rng.random((B, Nq, Nk)) < 0.6)
+    blocked[0, 3] = True            # fully blocked row -> must attend everywhere
+    blocked[1, 99] = True
+    blocked[0, 5] = True
+    blocked[0, 5, Nk - 1] = False   # a single open key at the very end
+    blocked[1, 7, 64:] = True       # open only inside the first tile
+    words = (Nk + 63) // 64 * 2
+    padded = torch.ones((B, Nq, words * 32), dtype=torch.bool)
+    padded[:, :, :Nk] = blocked
+    bits = (padded.view(B, Nq, words, 32).long() << torch.arange(32)).sum(-1)
+    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+    rowany = (~blocked).any(-1).to(torch.int32).flatten()
+    got = ops.mha_core(q.cuda(), k.cuda(), v.cuda(), bits.cuda(), rowany.cuda()).cpu()
+    assert rel_err(got, _mha_ref(q, k, v, blocked)) < 5e-6
+
+
+@pytest.mark.parametrize("hw", [24, 1050, 4200])
+def test_attn_mask_bits(hw):
+    from pairnet_b200 import ops
+    B, N = 2, 100
+    E = _t((B, N, 256), 19)
+    ldf = (hw + 63) // 64 * 64
+    Fl = torch.zeros((B, 256, ldf))
+    Fl[:, :, :hw] = _t((B, 256, hw), 20)
+    E[0, 4] = 0.0  # all-zero row: logits == 0 -> not < 0 -> every key open
+    Fl[1, :, :hw] = torch.where(Fl[1, :, :hw] > 0, Fl[1, :, :hw], -Fl[1, :, :hw])
+    E[1, 9] = -E[1, 9].abs()  # negative embed x positive features -> all blocked -> rowany 0
+    bits, rowany = ops.attn_mask_bits(E.cuda(), Fl.cuda(), hw)
+    got = ops.unpack_bits(bits, hw).cpu()
+    logits = torch.einsum("bqc,bcp->bqp", E.double(), Fl[:, :, :hw].double())
+    ref = logits < 0
+    sure = logits.abs() > 1e-4
+    assert torch.equal(got[sure], ref[sure])
+    assert (got != ref).float().mean() < 1e-5
+    assert not got[0, 4].any() and got[1, 9].all()
+    ra = rowany.cpu().view(B, N)
+    assert ra[1, 9] == 0 and ra[0, 4] == 1
+    full = ops.unpack_bits(bits, ldf).cpu()
+    assert full[:, :, hw:].all()  # padding keys are blocked
+
+
+def test_mask_pred():
+    from pairnet_b200 import ops
+    E, Fm = _t((2, 100, 256), 21), _t((2, 256, 23, 31), 22)
+    got = ops.mask_pred(E.cuda(), Fm.cuda()).cpu()
+    assert rel_err(got, torch.einsum("bqc,bchw->bqhw", E.double(), Fm.double())) < 2e-6
+
+
+def test_conv_tiny_against_reference_golden():
+    """weights/inputs regenerated from seeds; expected output produced by the REFERENCE ConvTiny."""
+    from oracle.head import OConvTiny
+    from oracle.make_golden import CONV_CASES
+    from oracle.weights import numpy_state_dict, numpy_tensor
+    from pairnet_b200 import ops
+    for tag, mid, B, N, seed in CONV_CASES:
+        g = np.load(os.path.join(GOLDEN, f"convtiny_ref_{tag}.npz"))
+        m = OConvTiny(mid_channels=mid)
+        m.load_state_dict(numpy_state_dict(m, seed))
+        x = torch.tanh(numpy_tensor((B, N, N), seed + 100))
+        got = ops.conv_tiny(x.cuda(), m.cuda()).cpu()
+        assert rel_err(got, g["out"]) < 1e-5, tag
+
+
+@pytest.mark.parametrize("N,K", [(100, 100), (200, 100), (37, 5), (100, 1), (64, 1024), (400, 100)])
+def test_topk_pairs_bit_exact(N, K):
+    from pairnet_b200 import ops
+    B = 3
+    imp = _t((B, N, N), 23 + N)
+    q = _t((B, N, 256), 24)
+    idx, sp, op, pair = ops.topk_pairs(imp.cuda(), K, q.cuda())
+    ref_v, ref_i = torch.topk(imp.flatten(1), K)
+    assert torch.equal(idx.cpu(), ref_i)  # tie-free continuous values: exact, in order
+    assert torch.equal(sp.cpu(), torch.div(ref_i, N, rounding_mode="trunc"))
+    assert torch.equal(op.cpu(), torch.remainder(ref_i, N))
+    exp = torch.cat([torch.gather(q, 1, sp.cpu()[..., None].expand(-1, -1, 256)),
+                     torch.gather(q, 1, op.cpu()[..., None].expand(-1, -1, 256))], 1)
+    assert torch.equal(pair.cpu(), exp)
+
+
+def test_topk_pairs_ties_negative_and_special_values():
+    from oracle.head import stable_topk
+    from pairnet_b200 import ops
+    N, K = 50, 100
+    rng = np.random.default_rng(3)
+    imp = torch.from_numpy(rng.integers(-3, 4, size=(2, N, N)).astype(np.float32))  # massive ties
+    imp[0, 0, 0] = float("inf")
+    imp[0, 7, 7] = -0.0
+    imp[1] = -imp[1].abs() - 1.0  # all negative
+    idx, sp, op, _ = ops.topk_pairs(imp.cuda(), K)
+    for b in range(2):
+        assert idx[b].cpu().tolist() == stable_topk(imp[b].flatten().numpy(), K).tolist()
+    const = torch.full((1, N, N), 0.25)
+    idx, _, _, _ = ops.topk_pairs(const.cuda(), K)
+    assert idx[0].cpu().tolist() == list(range(K))  # all equal -> lowest flat indices, ascending
+
+
+def test_gather_rows_bit_exact():
+    from pairnet_b200 import ops
+    src = _t((2, 100, 134), 25)
+    idx = torch.from_numpy(np.random.default_rng(1).integers(0, 100, size=(2, 100)))
+    assert torch.equal(ops.gather_rows(src.cuda(), idx.cuda()).cpu(),
+                       torch.gather(src, 1, idx[..., None].expand(-1, -1, 134)))
+    seg = _t((2, 100, 20, 28), 26)
+    assert torch.equal(ops.gather_rows(seg.cuda(), idx.cuda()).cpu(),
+                       torch.gather(seg, 1, idx[..., None, None].expand(-1, -1, 20, 28)))
+
+
+def test_error_conventions():
+    from pairnet_b200 import _native as nat, ops
+    with pytest.raises(nat.NativeError):  # K > N*N
+        ops.topk_pairs(torch.zeros(1, 4, 4, device="cuda"), 100)
+    with pytest.raises(nat.NativeError):  # K not a multiple of the GEMM k-tile
+        ops.linear(torch.zeros(8, 100, device="cuda"), torch.zeros(8, 100, device="cuda"))
+    assert b"gemm" in nat.load().pn_last_error_string()

@@ -1,0 +1,66 @@
+"""CPU: the oracle against the committed golden vectors (ConvTiny fixtures were produced by the
+REFERENCE's own ``cnn_factory.ConvTiny``; head fixtures are the oracle's own regression anchors)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.head import OConvTiny, stable_topk
+from oracle.make_golden import CONV_CASES, HEAD_CASES, build_small_head, small_head_inputs
+from oracle.weights import numpy_state_dict, numpy_tensor
+from tests.util import GOLDEN, rel_err
+
+
+@pytest.mark.parametrize("tag,mid,B,N,seed", CONV_CASES)
+def test_convtiny_oracle_matches_reference_golden(tag, mid, B, N, seed):
+    g = np.load(os.path.join(GOLDEN, f"convtiny_ref_{tag}.npz"))
+    m = OConvTiny(mid_channels=mid).eval()
+    m.load_state_dict(numpy_state_dict(m, seed))
+    x = torch.tanh(numpy_tensor((B, N, N), seed + 100))
+    with torch.no_grad():
+        y = m(x)
+    assert y.shape == (B, N, N)
+    assert rel_err(y, g["out"]) < 1e-5
+
+
+def test_convtiny_oracle_equals_live_reference_if_present():
+    ref_path = "/root/reference/pairnet/models/frameworks/cnn_factory.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference tree not present on this box")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_cnn_factory", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    r = ref.ConvTiny().eval()
+    r.load_state_dict(numpy_state_dict(r, 5))
+    o = OConvTiny().eval()
+    o.load_state_dict(r.state_dict())
+    x = torch.tanh(numpy_tensor((1, 50, 50), 6))
+    with torch.no_grad():
+        assert torch.equal(r(x), o(x))
+
+
+@pytest.mark.parametrize("tag,B,hw4,seed", HEAD_CASES[1:])
+def test_head_oracle_regression(tag, B, hw4, seed):
+    g = np.load(os.path.join(GOLDEN, f"head_small_{tag}.npz"))
+    head = build_small_head()
+    mf, mems = small_head_inputs(B, hw4, seed)
+    tr = {}
+    with torch.no_grad():
+        cls, msk = head.forward_from_memories(mf, mems, trace=tr)
+    assert rel_err(cls["rel"], g["rel"]) < 1e-4
+    assert rel_err(cls["cls"], g["cls"]) < 1e-4
+    assert rel_err(cls["importance"], g["importance"]) < 1e-4
+    assert rel_err(msk["mask"][:, :, ::4, ::4], g["mask_sub4"]) < 1e-4
+    # indices: equal except for near-ties
+    same = (tr["sub_pos"].numpy() == g["sub_pos"]) & (tr["obj_pos"].numpy() == g["obj_pos"])
+    assert same.mean() > 0.9
+
+
+def test_stable_topk_contract():
+    v = np.array([1.0, 3.0, 3.0, -1.0, 3.0, 2.0], dtype=np.float32)
+    assert stable_topk(v, 4).tolist() == [1, 2, 4, 5]
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1000).astype(np.float32)
+    assert stable_topk(x, 50).tolist() == torch.topk(torch.from_numpy(x), 50).indices.tolist()
