@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the Pair-Net hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): Pair-Net R50 / Mask2Former, 100 object + 100 relation queries,
+bs = 2 per GPU, synthetic 800x1333 images, fp32.  One "step" = one forward of the whole detector
+(ResNet-50 + MSDeformAttn pixel decoder in PyTorch/cuDNN, then the hand-written CUDA head:
+masked-attention decoder -> Pair Proposal Network -> Relation Fusion).  Metric: images/sec.
+
+* value      : device-resident inputs, whole forward replayed as one CUDA graph, CUDA-event timed.
+* e2e        : the same through the public API (`PSGTr.forward_dummy`-equivalent) from PINNED HOST
+               images, H2D + D2H of the result inside the timed region.
+* roofline   : the dominant hand-written kernel (memory-side K/V projection GEMM), timed live.
+* cpu_baseline / --impl reference : the torch CPU oracle (restatement of the reference forward) on
+               the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+IMG_H, IMG_W, PER_GPU_BATCH = 800, 1333, 2
+METRIC = "images/sec Pair-Net R50 @100 queries (bs=2/GPU, 800x1333 synthetic, fp32 forward)"
+WORKLOAD = "Pair-Net R50, 100 queries, bs=2, 800x1333 synthetic, fp32, 1xB200 (BASELINE configs[1])"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU oracle leg")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--ppn-microbench", action="store_true", help="also run BASELINE config 5 (PPN only)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_setup(n_gpus, init=True):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and init:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def max_over_ranks(value, world, device):
+    """max over ranks of a python float (device-timed milliseconds)."""
+    if world == 1:
+        return value
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def build_model(device):
+    from pairnet_b200.registry import Config, build_detector
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_r50_b200.py"))
+    torch.manual_seed(10086)  # the reference's fixed seed (tools/train.py:204)
+    model = build_detector(cfg.model)
+    model.init_weights()
+    return model.to(device).eval()
+
+
+def synthetic_images(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, IMG_H, IMG_W, generator=g)
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_model():
+    from oracle.head import OPSGTr
+    torch.manual_seed(10086)
+    m = OPSGTr()
+    m.bbox_head.init_weights()
+    return m.eval()
+
+
+def time_cpu_oracle(steps, warmup, images_per_step=1, budget_s=240.0):
+    """images/sec of the torch CPU restatement of the reference forward (all host threads)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = cpu_oracle_model()
+    img = synthetic_images(images_per_step, 0)
+    times = []
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        m.forward_dummy(img)
+        first = time.perf_counter() - t0
+        done_warm = 1
+        while done_warm < warmup and first * (done_warm + 1) < budget_s / 4:
+            m.forward_dummy(img)
+            done_warm += 1
+        max_steps = max(1, min(steps, int(budget_s / max(first, 1e-3))))
+        for _ in range(max_steps):
+            t0 = time.perf_counter()
+            m.forward_dummy(img)
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return dict(value=images_per_step * len(times) / total, steps=len(times), warmup=done_warm,
+                ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(), images_per_step=images_per_step)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    r = time_cpu_oracle(args.steps, args.warmup, images_per_step=1)
+    sample = (f"{r['steps']} timed steps x 1 synthetic 800x1333 image through the whole detector on the host CPU "
+              f"(oracle port of the reference forward; requested steps={args.steps})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": 1, "device": "cpu"},
+        "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def time_steps(step_fn, steps, flush_buf, stream):
+    """Σ over steps of the CUDA-event time of `step_fn`, with an L2 flush (untimed) between steps."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in evs:
+        flush_buf.add_(1)  # 256 MiB read+write > 126 MB L2
+        s.record(stream)
+        step_fn()
+        e.record(stream)
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in evs]
+
+
+def dominant_kernel_roofline(model, device, pk):
+    """K/V projection of the 100x167 memory level: gemm_store_kernel<128,128,16,8,8> on
+    M = 2*16700 tokens, two problems (K and V), N = K = 256 -> 2*2*M*256*256 flops per launch."""
+    from pairnet_b200 import _native as nat
+    import ctypes as C
+    lib = nat.load()
+    M, d = PER_GPU_BATCH * 100 * 167, 256
+    x = torch.randn(M, d, device=device)
+    w = torch.randn(2 * d, d, device=device) * 0.05
+    b = torch.zeros(2 * d, device=device)
+    y = torch.empty(M, 2 * d, device=device)
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+
+    def launch():  # one launch, N = 512 (K and V weights stacked) == the two-problem launch's flops
+        nat.check(lib.pn_linear(x.data_ptr(), d, w.data_ptr(), b.data_ptr(), None, y.data_ptr(), 2 * d, M, 2 * d, d, 0,
+                                st), "pn_linear")
+    for _ in range(3):
+        launch()
+    ts = time_steps(launch, 10, flush, torch.cuda.current_stream())
+    ms = statistics.mean(ts)
+    flops = 2.0 * M * (2 * d) * d
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_store_kernel<128,128,16,8,8> (K/V projection, level 100x167)",
+            "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+            "traffic": None, "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": pk["source"],
+            "note": "exact-fp32 FFMA kernel measured against the dense bf16 tensor peak; fp32 FFMA peak ~75 TFLOP/s"}
+
+
+def ppn_microbench(device, pk):
+    """BASELINE config 5a: pair matrix + top-k only, N in {100,200,400}, d=256, k=100."""
+    import torch.nn.functional as F
+    from pairnet_b200 import ops
+    out = []
+    for N, Bm in ((100, 4096), (200, 2048), (400, 1024)):
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        s = F.normalize(torch.randn(Bm, N, 256, generator=g)).to(device)
+        o = F.normalize(torch.randn(Bm, N, 256, generator=g)).to(device)
+        plan = ops.PpnPlan(Bm, N, 100, device)
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+        for _ in range(3):
+            plan.run_embeds(s, o)
+        ts = time_steps(lambda: plan.run_embeds(s, o), 10, flush, torch.cuda.current_stream())
+        ms = statistics.mean(ts)
+        bytes_per_img = 2 * N * 256 * 4 + N * N * 4 + 2 * 100 * 8
+        gbs = Bm * bytes_per_img / (ms * 1e-3) / 1e9
+        out.append({"N": N, "batch": Bm, "ms": ms, "algorithmic_bytes_per_image": bytes_per_img, "achieved_gbs": gbs,
+                    "frac_of_hbm_peak": gbs / pk["hbm_gbs"]})
+    return out
+
+
+def run_b200(args, rank, world, local):
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    pk = peaks()
+    from pairnet_b200.detector import GraphedForward
+    model = build_model(device)
+    head = model.bbox_head
+    imgs_host = synthetic_images(PER_GPU_BATCH, 10086 + rank).pin_memory()
+    imgs_dev = imgs_host.to(device)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)  # 256 MiB
+    stream = torch.cuda.current_stream()
+
+    def forward(x):
+        cls, msk = model.forward_dummy(x)
+        sp, op = head.last_pairs
+        return cls, msk, sp, op
+
+    with torch.no_grad():
+        forward(imgs_dev)  # builds workspaces, cuDNN autotune, positional tables
+        torch.cuda.synchronize()
+        launches_per_step = head.last_launch_count
+        runner = forward if args.no_graph else GraphedForward(forward, imgs_dev, warmup=2)
+
+        # ---- stage breakdown (eager, untimed region; informational)
+        def ev_time(fn, n=5):
+            fn()
+            ts = time_steps(fn, n, flush, stream)
+            return statistics.mean(ts)
+        feats = model.extract_feat(imgs_dev)
+        mf, mems = head.pixel_decoder(feats)
+        breakdown = {
+            "backbone_ms": ev_time(lambda: model.extract_feat(imgs_dev)),
+            "pixel_decoder_ms": ev_time(lambda: head.pixel_decoder(feats)),
+            "head_cuda_ms": ev_time(lambda: head.forward_from_memories(mf, mems)),
+        }
+        del feats, mf, mems
+
+        # ---- device-resident throughput
+        for _ in range(max(args.warmup, 3)):
+            runner(imgs_dev)
+        torch.cuda.synchronize()
+        barrier(world)
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local)
+        clocks.start()
+        t_wall = time.perf_counter()
+        step = (lambda: forward(imgs_dev)) if args.no_graph else (lambda: runner())
+        ts = time_steps(step, args.steps, flush, stream)
+        torch.cuda.synchronize()
+        barrier(world)
+        wall_s = time.perf_counter() - t_wall
+        dev_ms = max_over_ranks(sum(ts), world, device)
+        value = world * PER_GPU_BATCH * args.steps / (dev_ms * 1e-3)
+
+        # ---- end-to-end through the public API: pinned host images in, result tensors out to pinned host
+        res_keys = ("sub", "obj", "cls", "rel", "importance")
+        cls0, _, sp0, op0 = runner(imgs_dev)
+        host_out = {k: torch.empty(cls0[k].shape, dtype=cls0[k].dtype).pin_memory() for k in res_keys}
+        host_out["sub_pos"] = torch.empty(sp0.shape, dtype=sp0.dtype).pin_memory()
+        host_out["obj_pos"] = torch.empty(op0.shape, dtype=op0.dtype).pin_memory()
+        h2d = imgs_host.numel() * imgs_host.element_size()
+        d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+        static_in = runner.static_in if not args.no_graph else imgs_dev
+
+        def e2e_step():
+            static_in.copy_(imgs_host, non_blocking=True)
+            cls, _, sp, op = runner(static_in)
+            for k in res_keys:
+                host_out[k].copy_(cls[k], non_blocking=True)
+            host_out["sub_pos"].copy_(sp, non_blocking=True)
+            host_out["obj_pos"].copy_(op, non_blocking=True)
+            stream.synchronize()  # the caller holds the result on the host
+
+        for _ in range(3):
+            e2e_step()
+        barrier(world)
+        te = time_steps(e2e_step, args.steps, flush, stream)
+        barrier(world)
+        e2e_ms = max_over_ranks(sum(te), world, device)
+        e2e_value = world * PER_GPU_BATCH * args.steps / (e2e_ms * 1e-3)
+        clk = clocks.stop()
+
+        roof = dominant_kernel_roofline(model, device, pk) if rank == 0 else None
+        micro = ppn_microbench(device, pk) if (rank == 0 and args.ppn_microbench) else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = time_cpu_oracle(steps=3, warmup=1, images_per_step=1, budget_s=30.0)
+        cpu = {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} x 1 synthetic 800x1333 image, whole detector forward, torch CPU oracle "
+                         f"({r['ms_per_step']:.0f} ms/image)"}
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": world * PER_GPU_BATCH,
+                   "image": [IMG_H, IMG_W], "queries": 100, "parallelism": f"dp{world} (replicas, no forward collective)",
+                   "l2_flush": "256 MiB read+write between timed steps (outside the event pair)",
+                   "cuda_graph": not args.no_graph,
+                   "upstream": "ResNet-50 + MSDeformAttn pixel decoder in PyTorch (cuDNN TF32 conv default, fp32 matmul)"},
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps,
+                "result": "all_cls_scores (sub,obj,cls,rel,importance) + sub_pos/obj_pos to pinned host; mask tensors stay on device"},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "clocks": clk,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "breakdown_ms": breakdown,
+        "wall_s_timed_region": wall_s,
+    }
+    if micro is not None:
+        line["ppn_microbench"] = micro
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_setup(args.gpus, init=args.impl != "reference")
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_b200(args, rank, world, local)
+    finally:
+        if world > 1 and args.impl != "reference":
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
