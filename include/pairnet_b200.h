@@ -72,6 +72,11 @@ typedef struct { const float* w[3]; const float* b[3]; int mid_channels; } PnCon
 /* ------------------------------------------------------------------ library */
 PN_API int pn_version(void);
 PN_API const char* pn_last_error_string(void);
+/* process-wide options. PN_OPT_TENSOR_CORES (default 1): memory-side GEMMs with >= 1024 rows run on the
+ * tcgen05 3xTF32 kernel; 0 = exact-fp32 FFMA kernels everywhere (A/B and parity studies). */
+#define PN_OPT_TENSOR_CORES 0
+PN_API int pn_set_option(int key, int value);
+PN_API int pn_get_option(int key);
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -103,6 +108,12 @@ PN_API int pn_mask_pred(const float* E, const float* F, float* mask_pred, int B,
 /* y[M,N] = act(x[M,K] W[N,K]^T + b) (+ resid[M,N]);  relu: 0/1 */
 PN_API int pn_linear(const float* x, int ldx, const float* w, const float* b, const float* resid,
               float* y, int ldy, int M, int N, int K, int relu, pn_stream_t stream);
+/* Tensor-core variant of pn_linear for large M (tcgen05.mma kind::tf32, TMA-staged tiles, TMEM accumulator).
+ * passes = 3: operands are split hi/lo ("3xTF32") so the result matches fp32 FFMA to ~1e-6;
+ * passes = 1: plain TF32.  K % 32 == 0, ldx/ldy % 4 == 0.  ws >= pn_linear_tc_workspace_bytes(M,N,K). */
+PN_API size_t pn_linear_tc_workspace_bytes(int M, int N, int K);
+PN_API int pn_linear_tc(const float* x, int ldx, const float* w, const float* b, float* y, int ldy,
+                        int M, int N, int K, int passes, void* ws, size_t ws_bytes, pn_stream_t stream);
 /* y = LayerNorm(x + resid) over 256 channels (resid may be NULL) */
 PN_API int pn_add_layernorm(const float* x, const float* resid, const float* gamma, const float* beta,
                      float* y, int M, pn_stream_t stream);

@@ -86,6 +86,8 @@ SIGNATURES = {
     "pn_version": (i32, []),
     "pn_last_error_string": (C.c_char_p, []),
     "pn_last_launch_count": (i32, []),
+    "pn_set_option": (i32, [i32, i32]),
+    "pn_get_option": (i32, [i32]),
     "pn_device_info": (i32, [P(i32), P(i32), P(i32)]),
     "pn_sine_posenc": (i32, [vp, i32, i32, vp]),
     "pn_level_prep": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
@@ -93,6 +95,8 @@ SIGNATURES = {
     "pn_attn_mask_bits": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "pn_mask_pred": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "pn_linear": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "pn_linear_tc_workspace_bytes": (sz, [i32, i32, i32]),
+    "pn_linear_tc": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
     "pn_add_layernorm": (i32, [vp, vp, vp, vp, vp, i32, vp]),
     "pn_mha_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_mha_core": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, vp, sz, vp]),

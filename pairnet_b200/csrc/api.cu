@@ -11,6 +11,8 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
+static int g_options[OPT_COUNT] = {1, 0, 0, 0};
+int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -170,8 +172,11 @@ static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
   return 0;
 }
 
+constexpr int TC_MIN_ROWS = 1024;  // memory levels with fewer tokens stay on the FFMA GEMM
 struct M2FBuffers {
   float *X[PN_MAX_LEVELS], *XP[PN_MAX_LEVELS], *Fl[PN_MAX_LEVELS], *pos[PN_MAX_LEVELS];
+  float *Xlo[PN_MAX_LEVELS], *XPlo[PN_MAX_LEVELS];  // 3xTF32 low parts (tensor-core K/V projection)
+  float *Whi, *Wlo;                                  // split [Wk;Wv] of the current layer [512,256]
   float *K, *V;
   uint32_t* bits; int* rowany;
   float *x, *xpos, *xn, *e1, *e2, *e;
@@ -182,9 +187,13 @@ static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2F
   for (int l = 0; l < p.L; ++l) {
     b.X[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
     b.XP[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
+    b.Xlo[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
+    b.XPlo[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
     b.Fl[l] = ws.take<float>((size_t)p.B * D * p.ldf[l]);
     b.pos[l] = (in && in->pos[l]) ? nullptr : ws.take<float>((size_t)p.hw[l] * D);
   }
+  b.Whi = ws.take<float>((size_t)2 * D * D);
+  b.Wlo = ws.take<float>((size_t)2 * D * D);
   b.K = ws.take<float>((size_t)p.B * p.maxhw * D);
   b.V = ws.take<float>((size_t)p.B * p.maxhw * D);
   b.bits = ws.take<uint32_t>((size_t)p.M * (p.maxldf / 32));
@@ -216,7 +225,9 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
       PN_TRY(launch_sine_posenc(b.pos[l], in->h[l], in->w[l], st));
       pos = b.pos[l];
     }
-    PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st));
+    const bool tc = get_option(OPT_TENSOR_CORES) && p.B * p.hw[l] >= TC_MIN_ROWS;
+    PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st,
+                             tc ? b.Xlo[l] : nullptr, tc ? b.XPlo[l] : nullptr));
     PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
                                       st));
   }
@@ -244,8 +255,16 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
       PN_REQUIRE(e == cudaSuccess, (int)e, "mask trace copy: %s", cudaGetErrorString(e));
     }
     // K/V projections of this layer's memory level: k = (mem + lvl + pos) Wk^T, v = (mem + lvl) Wv^T
-    {
-      const int Mk = p.B * p.hw[l];
+    const int Mk = p.B * p.hw[l];
+    if (get_option(OPT_TENSOR_CORES) && Mk >= TC_MIN_ROWS) {
+      // tcgen05 path: TMA-staged tiles, UMMA kind::tf32 with hi/lo split operands (fp32 parity)
+      PN_TRY(launch_split_tf32(Lw.cross_attn.in_proj_w + (size_t)D * D, b.Whi, b.Wlo, (size_t)2 * D * D, st));
+      UmmaOperand o[2] = {
+          {b.XP[l], b.XPlo[l], D, b.Whi, b.Wlo, D, Lw.cross_attn.in_proj_b + D, b.K, D, Mk, D, D},
+          {b.X[l], b.Xlo[l], D, b.Whi + (size_t)D * D, b.Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, b.V, D,
+           Mk, D, D}};
+      PN_TRY(launch_umma_gemm(o, 2, 3, st));
+    } else {
       GemmBatch g{};
       g.p[0] = make_linear(b.XP[l], D, Lw.cross_attn.in_proj_w + (size_t)D * D, Lw.cross_attn.in_proj_b + D, b.K, D,
                            Mk, D, D);
@@ -397,6 +416,12 @@ using namespace pn;
 extern "C" {
 
 int pn_version(void) { return PN_VERSION; }
+int pn_set_option(int key, int value) {
+  PN_REQUIRE(key >= 0 && key < OPT_COUNT, PN_ERR_BAD_ARG, "pn_set_option: unknown key %d", key);
+  g_options[key] = value;
+  return 0;
+}
+int pn_get_option(int key) { return get_option(key); }
 const char* pn_last_error_string(void) { return g_err; }
 int pn_last_launch_count(void) { return g_launches; }
 
@@ -443,6 +468,28 @@ int pn_linear(const float* x, int ldx, const float* w, const float* b, const flo
   g.p[0] = make_linear(x, ldx, w, b, y, ldy, M, N, K, relu, resid, ldy);
   g.count = 1;
   return launch_gemm(g, as_stream(stream));
+}
+
+size_t pn_linear_tc_workspace_bytes(int M, int N, int K) {
+  Workspace ws(nullptr, 0);
+  ws.take<float>((size_t)M * K); ws.take<float>((size_t)M * K);
+  ws.take<float>((size_t)N * K); ws.take<float>((size_t)N * K);
+  return ws.off + 256;
+}
+
+int pn_linear_tc(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
+                 int passes, void* ws, size_t ws_bytes, pn_stream_t stream) {
+  PN_REQUIRE(x && w && y && ws, PN_ERR_BAD_ARG, "linear_tc: null pointer");
+  PN_REQUIRE(ldx == K, PN_ERR_UNSUPPORTED, "linear_tc: x must be dense (ldx == K)");
+  Workspace W(ws, ws_bytes);
+  float* xh = W.take<float>((size_t)M * K); float* xl = W.take<float>((size_t)M * K);
+  float* wh = W.take<float>((size_t)N * K); float* wl = W.take<float>((size_t)N * K);
+  PN_REQUIRE(W.ok() && xh && xl && wh && wl, PN_ERR_WORKSPACE, "linear_tc: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  PN_TRY(launch_split_tf32(x, xh, xl, (size_t)M * K, st));
+  PN_TRY(launch_split_tf32(w, wh, wl, (size_t)N * K, st));
+  UmmaOperand o{xh, xl, K, wh, wl, K, b, y, ldy, M, N, K};
+  return launch_umma_gemm(&o, 1, passes, st);
 }
 
 int pn_add_layernorm(const float* x, const float* resid, const float* gamma, const float* beta, float* y, int M,

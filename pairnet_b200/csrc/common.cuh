@@ -87,6 +87,17 @@ int launch_gemm_nmajor_store(const GemmProb& p, cudaStream_t st);              /
 int launch_gemm_nmajor_maskbits(const float* E, const float* F, uint32_t* bits, int* rowany, int B,
                                 int N, int hw, int ldf, cudaStream_t st);
 
+// tcgen05 (TMA + UMMA kind::tf32) GEMM: C = A . W^T + bias with pre-split hi/lo operands (umma_gemm.cu)
+struct UmmaOperand {
+  const float* a_hi; const float* a_lo; int lda;   // A [M,K]
+  const float* w_hi; const float* w_lo; int ldw;   // W [N,K]
+  const float* bias;
+  float* C; int ldc;
+  int M, N, K;
+};
+int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st);
+
 struct LnArgs {
   const float* x;          // [nparts][M][256]
   int nparts;
@@ -120,7 +131,10 @@ int launch_mha(const MhaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
 
 int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
-                      int B, int hw, cudaStream_t st);
+                      int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
+// runtime options (pn_set_option)
+enum { OPT_TENSOR_CORES = 0, OPT_COUNT = 4 };
+int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);
 int launch_bcast_rows(const float* a, const float* b, float* out, float* out_sum, int B, int N,

@@ -183,10 +183,18 @@ int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st) {
 }
 
 // mem [B,256,hw] -> x [B,hw,256] (+ level_embed) ; xp = x + pos.   32x32 smem transpose tiles.
+__device__ __forceinline__ float rna_tf32f(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+// x_lo/xp_lo != null: 3xTF32 operand form for the tcgen05 K/V projection -- x/xp receive hi = rna_tf32(v),
+// x_lo/xp_lo receive rna_tf32(v - hi).
 __global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict__ mem,
                                                           const float* __restrict__ level_embed,
                                                           const float* __restrict__ pos, float* __restrict__ x,
-                                                          float* __restrict__ xp, int hw) {
+                                                          float* __restrict__ xp, float* __restrict__ x_lo,
+                                                          float* __restrict__ xp_lo, int hw) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -204,16 +212,26 @@ __global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict
     if (p < hw) {
       const float v = tile[tx][ty + r * 8] + __ldg(level_embed + c);
       const size_t o = ((size_t)b * hw + p) * D + c;
-      x[o] = v;
-      xp[o] = v + __ldg(pos + (size_t)p * D + c);
+      const float vp = v + __ldg(pos + (size_t)p * D + c);
+      if (x_lo) {
+        const float h = rna_tf32f(v), hp = rna_tf32f(vp);
+        x[o] = h;
+        x_lo[o] = rna_tf32f(v - h);
+        xp[o] = hp;
+        xp_lo[o] = rna_tf32f(vp - hp);
+      } else {
+        x[o] = v;
+        xp[o] = vp;
+      }
     }
   }
 }
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp, int B,
-                      int hw, cudaStream_t st) {
+                      int hw, cudaStream_t st, float* x_lo, float* xp_lo) {
   PN_REQUIRE(mem && level_embed && pos && x && xp && B > 0 && hw > 0, PN_ERR_BAD_ARG, "level_prep: bad args");
   dim3 grid(cdiv(hw, 32), D / 32, B);
-  level_prep_kernel<<<grid, 256, 0, st>>>(mem, level_embed, pos, x, xp, hw);
+  PN_REQUIRE((x_lo == nullptr) == (xp_lo == nullptr), PN_ERR_BAD_ARG, "level_prep: lo outputs come in pairs");
+  level_prep_kernel<<<grid, 256, 0, st>>>(mem, level_embed, pos, x, xp, x_lo, xp_lo, hw);
   return check_launch("level_prep_kernel");
 }
 

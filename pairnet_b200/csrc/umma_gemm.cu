@@ -1,0 +1,334 @@
+// tcgen05 tensor-core GEMM for the memory-side projections:  C[M,N] = A[M,K] . W[N,K]^T + bias
+//
+// Blackwell-native structure (sm_100a): TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages 128 x 32-float
+// operand tiles in shared memory through a 3-deep mbarrier ring; one elected thread issues
+// tcgen05.mma.kind::tf32 (M=128, N=128, K=8) with the fp32 accumulator in TMEM; four epilogue warps read the
+// accumulator back with tcgen05.ld, add the bias and store 128-bit rows.
+//
+// fp32 parity ("3xTF32"): every operand is pre-split into hi = rna_tf32(x) and lo = rna_tf32(x - hi);
+// the accumulator receives lo*hi + hi*lo + hi*hi, i.e. all product bits down to ~2^-22 relative, so the
+// result matches an fp32 FFMA GEMM to ~1e-6 while running on the tensor pipe.  `passes = 1` (hi*hi only)
+// is plain TF32.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pn {
+namespace umma {
+
+constexpr int BM = 128, BN = 128, BK = 32;  // BK fp32 = 128 B = one SWIZZLE_128B row
+constexpr int STAGES = 3;
+constexpr int UMMA_K = 8;                   // kind::tf32: 32 bytes of K per instruction
+constexpr int TILE_BYTES = BM * BK * 4;     // 16 KiB (BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES; // a_hi, a_lo, b_hi, b_lo
+constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue
+constexpr int TMEM_COLS = 128;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile [rows][128 B], SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 128
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // D format: F32
+  d |= 2u << 7;                    // A format: TF32
+  d |= 2u << 10;                   // B format: TF32
+  d |= (uint32_t)(BN >> 3) << 17;  // N
+  d |= (uint32_t)(BM >> 4) << 24;  // M
+  return d;
+}
+
+struct Problem {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;  // A [M,K], W [N,K]; box 32 x 128, SWIZZLE_128B
+  const float* bias;
+  float* C;
+  int M, N, K, ldc;
+};
+constexpr int MAX_PROBLEMS = 2;
+struct Params {
+  Problem p[MAX_PROBLEMS];
+  int passes;  // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ Params prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const Problem& P = prm.p[blockIdx.z];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= P.M || n0 >= P.N) return;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = P.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp allocates the accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        const uint32_t bytes = (prm.passes == 3) ? STAGE_BYTES : 2 * TILE_BYTES;
+        mbar_expect_tx(&full_bar[s], bytes);
+        tma_load_2d(st + 0 * TILE_BYTES, &P.a_hi, &full_bar[s], kb * BK, m0);
+        tma_load_2d(st + 2 * TILE_BYTES, &P.b_hi, &full_bar[s], kb * BK, n0);
+        if (prm.passes == 3) {
+          tma_load_2d(st + 1 * TILE_BYTES, &P.a_lo, &full_bar[s], kb * BK, m0);
+          tma_load_2d(st + 3 * TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(st + 0 * TILE_BYTES), a_lo = make_smem_desc(st + 1 * TILE_BYTES);
+        const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES), b_lo = make_smem_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance start address inside the swizzle row
+          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+          if (prm.passes == 3) {
+            umma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, first);
+            umma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
+            umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, first);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 -> TMEM lane quadrant (warp % 4)
+    const int quad = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + quad * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (row < P.M) {
+        float* dst = P.C + (size_t)row * P.ldc + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n + 3 < P.N) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]) + (P.bias ? __ldg(P.bias + n + 0) : 0.f);
+            o.y = __uint_as_float(v[j + 1]) + (P.bias ? __ldg(P.bias + n + 1) : 0.f);
+            o.z = __uint_as_float(v[j + 2]) + (P.bias ? __ldg(P.bias + n + 2) : 0.f);
+            o.w = __uint_as_float(v[j + 3]) + (P.bias ? __ldg(P.bias + n + 3) : 0.f);
+            *reinterpret_cast<float4*>(dst + j) = o;
+          } else {
+            for (int t = 0; t < 4; ++t)
+              if (n + t < P.N) dst[j + t] = __uint_as_float(v[j + t]) + (P.bias ? __ldg(P.bias + n + t) : 0.f);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- hi/lo split (round-to-nearest tf32) ---------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                          float* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 h, l;
+    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+    l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major fp32 matrix [rows, cols] with leading dimension ld (elements); box = 32 cols x 128 rows
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  PN_REQUIRE(fn, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  PN_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, PN_ERR_UNSUPPORTED, "umma: operand must be 16B aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace umma
+
+int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  PN_REQUIRE(x && hi && lo && n % 4 == 0, PN_ERR_BAD_ARG, "split_tf32: bad args");
+  PN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, PN_ERR_UNSUPPORTED, "split_tf32: alignment");
+  const size_t n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  blocks = blocks > 148 * 16 ? 148 * 16 : (blocks < 1 ? 1 : blocks);
+  umma::split_tf32_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n4);
+  return check_launch("split_tf32_kernel");
+}
+
+int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st) {
+  using namespace umma;
+  PN_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, PN_ERR_BAD_ARG, "umma: bad problem count");
+  PN_REQUIRE(passes == 1 || passes == 3, PN_ERR_BAD_ARG, "umma: passes must be 1 or 3");
+  Params prm{};
+  prm.passes = passes;
+  int maxM = 0, maxN = 0;
+  for (int i = 0; i < count; ++i) {
+    const UmmaOperand& o = ops[i];
+    PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || (o.a_lo && o.w_lo)), PN_ERR_BAD_ARG, "umma: null operand");
+    PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
+    PN_REQUIRE(o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C must be 16B aligned");
+    Problem& p = prm.p[i];
+    PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
+    PN_TRY(make_map(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
+    PN_TRY(make_map(&p.a_lo, passes == 3 ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
+    PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
+    p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
+    maxM = o.M > maxM ? o.M : maxM;
+    maxN = o.N > maxN ? o.N : maxN;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), count);
+  umma_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(prm);
+  return check_launch("umma_gemm_kernel");
+}
+
+}  // namespace pn

@@ -83,6 +83,20 @@ def linear(x, weight, bias=None, relu=False, resid=None):
     return y
 
 
+def linear_tc(x, weight, bias=None, passes=3):
+    """tcgen05 tensor-core linear (3xTF32 by default): x [M,K] @ weight[N,K]^T + bias."""
+    x, weight = _f32(x), _f32(weight)
+    M, K = x.shape
+    N = weight.shape[0]
+    lib = nat.load()
+    need = lib.pn_linear_tc_workspace_bytes(M, N, K)
+    ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    nat.check(lib.pn_linear_tc(x.data_ptr(), K, weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                               y.data_ptr(), N, M, N, K, passes, ws.data_ptr(), need, _stream(x)), "pn_linear_tc")
+    return y
+
+
 def add_layernorm(x, resid, gamma, beta):
     x = _f32(x)
     y = torch.empty_like(x)

@@ -215,3 +215,16 @@ def test_error_conventions():
     with pytest.raises(nat.NativeError):  # K not a multiple of the GEMM k-tile
         ops.linear(torch.zeros(8, 100, device="cuda"), torch.zeros(8, 100, device="cuda"))
     assert b"gemm" in nat.load().pn_last_error_string()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 256, 256), (1000, 256, 256), (4200, 512, 256), (333, 384, 1024)])
+def test_linear_tc_3xtf32_matches_fp32(M, N, K):
+    """tcgen05 GEMM (TMA + UMMA kind::tf32, hi/lo split): fp32-level accuracy; single pass = TF32 accuracy."""
+    from pairnet_b200 import ops
+    x, w, b = _t((M, K), 30), _t((N, K), 31, 0.1), _t((N,), 32)
+    ref = x.double() @ w.double().t() + b.double()
+    got3 = ops.linear_tc(x.cuda(), w.cuda(), b.cuda(), passes=3).cpu()
+    assert rel_err(got3, ref) < 2e-5  # tensor-core fp32 accumulation over K up to 1024
+    got1 = ops.linear_tc(x.cuda(), w.cuda(), b.cuda(), passes=1).cpu()
+    e1 = rel_err(got1, ref)
+    assert 1e-5 < e1 < 5e-3  # really went through TF32 tensor cores
