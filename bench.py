@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU oracle leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--ppn-microbench", action="store_true", help="also run BASELINE config 5 (PPN only)")
+    ap.add_argument("--profile", action="store_true",
+                    help="warm up, then run ONE eager forward between cudaProfilerStart/Stop and exit "
+                         "(for `ncu --profile-from-start off`)")
     return ap.parse_args()
 
 
@@ -284,6 +287,14 @@ def run_b200(args, rank, world, local):
         forward(imgs_dev)  # builds workspaces, cuDNN autotune, positional tables
         torch.cuda.synchronize()
         launches_per_step = head.last_launch_count
+        if args.profile:
+            forward(imgs_dev)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            forward(imgs_dev)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return
         runner = forward if args.no_graph else GraphedForward(forward, imgs_dev, warmup=2)
 
         # ---- stage breakdown (eager, untimed region; informational)

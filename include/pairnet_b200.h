@@ -212,6 +212,30 @@ PN_API int pn_relation_fusion_forward(const PnRelWeights* w, const float* pair_f
 PN_API int pn_gather_rows(const float* src, const int64_t* idx, float* dst, int B, int Nsrc, int R,
                    long long L, pn_stream_t stream);
 
+/* ------------------------------------------------------------------ upstream "next" row
+ * The 6-layer multi-scale deformable-attention encoder of mmdet's MSDeformAttnPixelDecoder
+ * (cfg configs/mask2former/pairnet.py:38-66; called from pairnet_head.py:262).  8 heads x 32. */
+typedef struct {
+  PnLinear sampling_offsets;   /* [8*L*P*2, 256] */
+  PnLinear attention_weights;  /* [8*L*P, 256] */
+  PnLinear value_proj, output_proj;
+  PnLinear ffn1, ffn2;         /* [ffn,256], [256,ffn] */
+  PnNorm norm[2];
+} PnMsdaEncoderLayer;
+typedef struct {
+  int num_layers, num_levels, num_points, ffn_dims;
+  PnMsdaEncoderLayer layers[PN_MAX_LAYERS];
+} PnMsdaEncoderWeights;
+/* x_in/x_out [B,nq,256] token-major (levels concatenated, low -> high res order of `h`,`w`);
+ * pos [nq,256] = sine position + level encoding.  Linears run on the tcgen05 3xTF32 GEMM. */
+PN_API size_t pn_msda_encoder_workspace_bytes(int B, int nq, int ffn_dims, int num_levels, int num_points);
+PN_API int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, const float* pos,
+                                   const int* h, const int* w_, float* x_out, int B, void* ws, size_t ws_bytes,
+                                   pn_stream_t stream);
+/* sampling core only: value [B,nq,256], ol [B*nq, 8*L*P*3] (offsets then attention logits) -> out [B*nq,256] */
+PN_API int pn_msda_sample(const float* value, const float* ol, float* out, const int* h, const int* w_,
+                          int num_levels, int num_points, int B, pn_stream_t stream);
+
 /* ------------------------------------------------------------------ whole hot path
  * CrossHead2.forward minus the pixel decoder (pairnet_head.py:264-417) in one call. */
 typedef struct {

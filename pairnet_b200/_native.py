@@ -78,6 +78,16 @@ class PnHeadOutputs(C.Structure):
                 ("trace_words", C.c_int)]
 
 
+class PnMsdaEncoderLayer(C.Structure):
+    _fields_ = [("sampling_offsets", PnLinear), ("attention_weights", PnLinear), ("value_proj", PnLinear),
+                ("output_proj", PnLinear), ("ffn1", PnLinear), ("ffn2", PnLinear), ("norm", PnNorm * 2)]
+
+
+class PnMsdaEncoderWeights(C.Structure):
+    _fields_ = [("num_layers", C.c_int), ("num_levels", C.c_int), ("num_points", C.c_int), ("ffn_dims", C.c_int),
+                ("layers", PnMsdaEncoderLayer * PN_MAX_LAYERS)]
+
+
 i32, i64, sz, vp = C.c_int, C.c_longlong, C.c_size_t, c_void_p
 P = C.POINTER
 
@@ -110,6 +120,9 @@ SIGNATURES = {
     "pn_relation_fusion_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "pn_relation_fusion_forward": (i32, [P(PnRelWeights), vp, vp, vp, i32, i32, vp, sz, vp]),
     "pn_gather_rows": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
+    "pn_msda_encoder_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
+    "pn_msda_encoder_forward": (i32, [P(PnMsdaEncoderWeights), vp, vp, P(i32), P(i32), vp, i32, vp, sz, vp]),
+    "pn_msda_sample": (i32, [vp, vp, vp, P(i32), P(i32), i32, i32, i32, vp]),
     "pn_head_workspace_bytes": (sz, [P(PnHeadWeights), P(PnM2FInputs)]),
     "pn_head_forward": (i32, [P(PnHeadWeights), P(PnM2FInputs), P(PnHeadOutputs), vp, sz, vp]),
 }

@@ -94,6 +94,8 @@ struct UmmaOperand {
   const float* bias;
   float* C; int ldc;
   int M, N, K;
+  float* C_lo;   // optional: emit the result pre-split (C = hi, C_lo = lo) for a chained 3xTF32 GEMM
+  int relu;
 };
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st);
@@ -110,6 +112,10 @@ struct LnArgs {
   const float* pos;        // [pos_mod][256] or null
   int pos_mod;
   float* ypos;             // y + pos[m % pos_mod] or null
+  float* y_hi;             // optional 3xTF32 split copies of y and ypos (tensor-core consumers)
+  float* y_lo;
+  float* ypos_hi;
+  float* ypos_lo;
   const float* gamma2;     // optional chained second LN (post_norm)
   const float* beta2;
   float* y2;

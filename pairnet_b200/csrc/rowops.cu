@@ -6,6 +6,11 @@
 
 namespace pn {
 
+__device__ __forceinline__ float rna_tf32f(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -47,6 +52,18 @@ __device__ __forceinline__ void store_row(const float (&v)[8], float* __restrict
   reinterpret_cast<float4*>(p)[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+__device__ __forceinline__ void store_split(const float (&v)[8], float* __restrict__ hi, float* __restrict__ lo,
+                                            int lane) {
+  float h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = rna_tf32f(v[i]);
+    l[i] = rna_tf32f(v[i] - h[i]);
+  }
+  store_row(h, hi, lane);
+  store_row(l, lo, lane);
+}
+
 // lane owns channels [4*lane, 4*lane+4) and [128+4*lane, 128+4*lane+4)
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   const int lane = threadIdx.x & 31;
@@ -74,12 +91,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   }
   ln_row(v, a.gamma, a.beta, lane);
   store_row(v, a.y + (size_t)m * D, lane);
-  if (a.ypos) {
+  if (a.y_hi) store_split(v, a.y_hi + (size_t)m * D, a.y_lo + (size_t)m * D, lane);
+  if (a.ypos || a.ypos_hi) {
     float t[8];
     load_row(t, a.pos + (size_t)(m % a.pos_mod) * D, lane);
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = v[i] + t[i];
-    store_row(t, a.ypos + (size_t)m * D, lane);
+    if (a.ypos) store_row(t, a.ypos + (size_t)m * D, lane);
+    if (a.ypos_hi) store_split(t, a.ypos_hi + (size_t)m * D, a.ypos_lo + (size_t)m * D, lane);
   }
   if (a.y2) {
     ln_row(v, a.gamma2, a.beta2, lane);
@@ -89,7 +108,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 
 int launch_layernorm(const LnArgs& a, cudaStream_t st) {
   PN_REQUIRE(a.x && a.gamma && a.beta && a.y && a.M > 0 && a.nparts >= 1, PN_ERR_BAD_ARG, "layernorm: bad args");
-  PN_REQUIRE(!a.ypos || (a.pos && a.pos_mod > 0), PN_ERR_BAD_ARG, "layernorm: ypos needs pos");
+  PN_REQUIRE(!(a.ypos || a.ypos_hi) || (a.pos && a.pos_mod > 0), PN_ERR_BAD_ARG, "layernorm: ypos needs pos");
+  PN_REQUIRE((a.y_hi == nullptr) == (a.y_lo == nullptr) && (a.ypos_hi == nullptr) == (a.ypos_lo == nullptr),
+             PN_ERR_BAD_ARG, "layernorm: split outputs come in hi/lo pairs");
   PN_REQUIRE(!a.y2 || (a.gamma2 && a.beta2), PN_ERR_BAD_ARG, "layernorm: y2 needs gamma2/beta2");
   layernorm_kernel<<<cdiv(a.M, 8), 256, 0, st>>>(a);
   return check_launch("layernorm_kernel");
@@ -183,11 +204,6 @@ int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st) {
 }
 
 // mem [B,256,hw] -> x [B,hw,256] (+ level_embed) ; xp = x + pos.   32x32 smem transpose tiles.
-__device__ __forceinline__ float rna_tf32f(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
-}
 // x_lo/xp_lo != null: 3xTF32 operand form for the tcgen05 K/V projection -- x/xp receive hi = rna_tf32(v),
 // x_lo/xp_lo receive rna_tf32(v - hi).
 __global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict__ mem,

@@ -105,11 +105,19 @@ __device__ __forceinline__ uint32_t make_idesc() {
   return d;
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 struct Problem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;  // A [M,K], W [N,K]; box 32 x 128, SWIZZLE_128B
   const float* bias;
   float* C;
+  float* C_lo;  // non-null: write the result pre-split for a following 3xTF32 GEMM (C = hi, C_lo = lo)
   int M, N, K, ldc;
+  int relu;
 };
 constexpr int MAX_PROBLEMS = 2;
 struct Params {
@@ -209,19 +217,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
       if (row < P.M) {
         float* dst = P.C + (size_t)row * P.ldc + n0 + c0;
+        float* dlo = P.C_lo ? P.C_lo + (size_t)row * P.ldc + n0 + c0 : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int n = n0 + c0 + j;
-          if (n + 3 < P.N) {
-            float4 o;
-            o.x = __uint_as_float(v[j + 0]) + (P.bias ? __ldg(P.bias + n + 0) : 0.f);
-            o.y = __uint_as_float(v[j + 1]) + (P.bias ? __ldg(P.bias + n + 1) : 0.f);
-            o.z = __uint_as_float(v[j + 2]) + (P.bias ? __ldg(P.bias + n + 2) : 0.f);
-            o.w = __uint_as_float(v[j + 3]) + (P.bias ? __ldg(P.bias + n + 3) : 0.f);
-            *reinterpret_cast<float4*>(dst + j) = o;
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float x = __uint_as_float(v[j + t]) + ((P.bias && n + t < P.N) ? __ldg(P.bias + n + t) : 0.f);
+            o[t] = P.relu ? fmaxf(x, 0.f) : x;
+          }
+          if (dlo) {
+            float h[4], l[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              h[t] = rna_tf32(o[t]);
+              l[t] = rna_tf32(o[t] - h[t]);
+            }
+            if (n + 3 < P.N) {
+              *reinterpret_cast<float4*>(dst + j) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(dlo + j) = make_float4(l[0], l[1], l[2], l[3]);
+            } else {
+              for (int t = 0; t < 4; ++t)
+                if (n + t < P.N) { dst[j + t] = h[t]; dlo[j + t] = l[t]; }
+            }
+          } else if (n + 3 < P.N) {
+            *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
           } else {
             for (int t = 0; t < 4; ++t)
-              if (n + t < P.N) dst[j + t] = __uint_as_float(v[j + t]) + (P.bias ? __ldg(P.bias + n + t) : 0.f);
+              if (n + t < P.N) dst[j + t] = o[t];
           }
         }
       }
@@ -237,11 +261,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 }
 
 // ---- hi/lo split (round-to-nearest tf32) ---------------------------------------------------------------
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                           float* __restrict__ lo, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
@@ -317,6 +336,8 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     PN_TRY(make_map(&p.a_lo, passes == 3 ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
+    p.C_lo = o.C_lo; p.relu = o.relu;
+    PN_REQUIRE(!o.C_lo || ((uintptr_t)o.C_lo & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C_lo must be 16B aligned");
     maxM = o.M > maxM ? o.M : maxM;
     maxN = o.N > maxN ? o.N : maxN;
   }

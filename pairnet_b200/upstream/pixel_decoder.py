@@ -3,12 +3,14 @@
 PyTorch plumbing (cuDNN / cuBLAS / ``grid_sample``), batch-first.  It produces ``mask_features`` and
 the three memories the CUDA hot path consumes.  Parameter names follow mmdet so checkpoints load.
 Not hand-written CUDA yet -- listed as the next row to take over."""
+import ctypes as C
 import math
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import _native as nat
 from ..registry import PLUGIN_LAYERS
 
 
@@ -150,6 +152,12 @@ class MSDeformAttnPixelDecoder(nn.Module):
         self.mask_feature = nn.Conv2d(feat_channels, out_channels, 1)
         self.num_outs = num_outs
         self._static = {}
+        # encoder implementation on CUDA tensors: "native" = pn_msda_encoder_forward (tcgen05 GEMMs + hand-written
+        # deformable sampling); "torch" = the PyTorch/grid_sample restatement below (kept for A/B tests)
+        self.encoder_impl = "native"
+        self._enc_key = None
+        self._enc_struct = None
+        self._enc_ws = None
 
     def init_weights(self):
         for m in list(self.input_convs) + list(self.lateral_convs) + list(self.output_convs):
@@ -164,6 +172,50 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 nn.init.xavier_normal_(p)
         for layer in self.encoder.layers:
             layer.attentions[0].init_weights()
+
+    def _native_weights(self):
+        params = list(self.encoder.parameters())
+        key = tuple(p.data_ptr() for p in params)
+        if key == self._enc_key:
+            return self._enc_struct
+        w = nat.PnMsdaEncoderWeights()
+        a0 = self.encoder.layers[0].attentions[0]
+        w.num_layers, w.num_levels, w.num_points = len(self.encoder.layers), a0.num_levels, a0.num_points
+        w.ffn_dims = self.encoder.layers[0].ffns[0].layers[0][0].out_features
+        if a0.num_heads != 8 or a0.embed_dims != nat.EMBED_DIMS:
+            raise NotImplementedError("native MSDeformAttn encoder is compiled for 8 heads x 32")
+
+        def lin(dst, m):
+            dst.w, dst.b = m.weight.data_ptr(), m.bias.data_ptr()
+        for i, layer in enumerate(self.encoder.layers):
+            a, d = layer.attentions[0], w.layers[i]
+            lin(d.sampling_offsets, a.sampling_offsets)
+            lin(d.attention_weights, a.attention_weights)
+            lin(d.value_proj, a.value_proj)
+            lin(d.output_proj, a.output_proj)
+            lin(d.ffn1, layer.ffns[0].layers[0][0])
+            lin(d.ffn2, layer.ffns[0].layers[1])
+            for j in range(2):
+                d.norm[j].gamma, d.norm[j].beta = layer.norms[j].weight.data_ptr(), layer.norms[j].bias.data_ptr()
+        self._enc_key, self._enc_struct = key, w
+        return w
+
+    def _native_encoder(self, x, pos, shapes):
+        lib = nat.load()
+        B, nq, _ = x.shape
+        w = self._native_weights()
+        L = len(shapes)
+        hs = (C.c_int * L)(*[s[0] for s in shapes])
+        wds = (C.c_int * L)(*[s[1] for s in shapes])
+        need = lib.pn_msda_encoder_workspace_bytes(B, nq, w.ffn_dims, w.num_levels, w.num_points)
+        if self._enc_ws is None or self._enc_ws.numel() < need or self._enc_ws.device != x.device:
+            self._enc_ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        nat.check(lib.pn_msda_encoder_forward(C.byref(w), x.data_ptr(), pos.data_ptr(), hs, wds, out.data_ptr(), B,
+                                              self._enc_ws.data_ptr(), self._enc_ws.numel(),
+                                              torch.cuda.current_stream(x.device).cuda_stream),
+                  "pn_msda_encoder_forward")
+        return out
 
     def _geometry(self, shapes, device, dtype):
         key = (tuple(shapes), str(device), dtype)
@@ -191,8 +243,11 @@ class MSDeformAttnPixelDecoder(nn.Module):
         pos_l, ref, norm = self._geometry(shapes, feats[0].device, feats[0].dtype)
         pos = torch.cat([p + self.level_encoding.weight[i][None, :] for i, p in pos_l], 0)[None]
         x = torch.cat(xs, 1)
-        for layer in self.encoder.layers:
-            x = layer(x, pos, ref, shapes, norm)
+        if x.is_cuda and self.encoder_impl == "native" and not torch.is_grad_enabled():
+            x = self._native_encoder(x.contiguous(), pos[0].contiguous(), shapes)
+        else:
+            for layer in self.encoder.layers:
+                x = layer(x, pos, ref, shapes, norm)
         mem = x.transpose(1, 2)
         outs, start = [], 0
         for h, w in shapes:

@@ -228,3 +228,44 @@ def test_linear_tc_3xtf32_matches_fp32(M, N, K):
     got1 = ops.linear_tc(x.cuda(), w.cuda(), b.cuda(), passes=1).cpu()
     e1 = rel_err(got1, ref)
     assert 1e-5 < e1 < 5e-3  # really went through TF32 tensor cores
+
+
+def _pixel_decoder(seed=3):
+    import os
+    from pairnet_b200.registry import Config, PLUGIN_LAYERS
+    from tests.util import ROOT
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_r50_b200.py"), import_custom_modules=False)
+    pd = dict(cfg.model.bbox_head.pixel_decoder)
+    pd.update(in_channels=[256, 512, 1024, 2048], feat_channels=256, out_channels=256)
+    torch.manual_seed(seed)
+    m = PLUGIN_LAYERS.build(pd)
+    m.init_weights()
+    with torch.no_grad():  # non-trivial offsets / attention logits (mmcv init zeroes those weights)
+        for layer in m.encoder.layers:
+            a = layer.attentions[0]
+            a.sampling_offsets.weight.normal_(0, 0.02)
+            a.attention_weights.weight.normal_(0, 0.05)
+    return m.cuda().eval()
+
+
+def test_msda_encoder_native_vs_torch():
+    """§8f-1 upstream row: native deformable encoder (tcgen05 GEMMs + sampling kernel) vs the PyTorch
+    grid_sample restatement on the same device, and vs the CPU oracle's pixel decoder."""
+    from oracle.bricks import OMSDeformAttnPixelDecoder
+    m = _pixel_decoder()
+    feats = [_t((2, 256, 40, 56), 41), _t((2, 512, 20, 28), 42), _t((2, 1024, 10, 14), 43), _t((2, 2048, 5, 7), 44)]
+    with torch.no_grad():
+        m.encoder_impl = "native"
+        mf_n, mem_n = m([f.cuda() for f in feats])
+        m.encoder_impl = "torch"
+        mf_t, mem_t = m([f.cuda() for f in feats])
+        o = OMSDeformAttnPixelDecoder().eval()
+        o.load_state_dict(m.state_dict())
+        mf_o, mem_o = o(feats)
+    for a, b in zip(mem_n, mem_t):
+        assert rel_err(a, b) < 2e-4
+    for a, b in zip(mem_n, mem_o):
+        assert rel_err(a, b) < 2e-4
+    # mask_feature passes through cuDNN convs that run TF32 by default on the GPU (upstream plumbing)
+    assert rel_err(mf_n, mf_t) < 1e-3
+    assert rel_err(mf_n, mf_o) < 5e-3
