@@ -29,15 +29,19 @@ __device__ __forceinline__ float rna_tf32m(float v) {
 
 // value [B,nq,256] ; ol [B*nq, ldo]: cols [0, 8*L*P*2) offsets ((h,l,p),xy), then 8*L*P attention logits ((h),(l,p))
 // out (hi, lo) [B*nq,256]
-__global__ void __launch_bounds__(256) msda_sample_kernel(const float* __restrict__ value, const float* __restrict__ ol,
-                                                           int ldo, float* __restrict__ out_hi, float* __restrict__ out_lo,
-                                                           const MsdaGeom g, int B) {
+// CTA = MSDA_TOK consecutive tokens (neighbours along x) of ONE head: neighbouring queries sample overlapping
+// taps of the same 128-byte head slice, so most gathers hit L1 instead of L2.
+constexpr int MSDA_TOK = 16;
+__global__ void __launch_bounds__(MSDA_TOK * 32) msda_sample_kernel(const float* __restrict__ value,
+                                                                     const float* __restrict__ ol, int ldo,
+                                                                     float* __restrict__ out_hi,
+                                                                     float* __restrict__ out_lo, const MsdaGeom g,
+                                                                     int B) {
   const int lane = threadIdx.x & 31;
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);  // (b*nq + q)*8 + head
-  if (wid >= (long long)B * g.nq * NH) return;
-  const int head = (int)(wid % NH);
-  const long long tok = wid / NH;
-  const int b = (int)(tok / g.nq), q = (int)(tok % g.nq);
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int q = blockIdx.x * MSDA_TOK + (threadIdx.x >> 5);
+  if (q >= g.nq) return;
+  const long long tok = (long long)b * g.nq + q;
   const int LP = g.L * g.P;
   // reference point of this token (cell centre of its own level, normalised)
   int ql = 0;
@@ -219,8 +223,8 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
       PN_TRY(launch_umma_gemm(o, 2, 3, st));
     }
     {
-      const long long warps = (long long)M * NH;
-      msda_sample_kernel<<<cdiv(warps, 8), 256, 0, st>>>(b.value, b.ol, ldo, b.att_hi, b.att_lo, g, B);
+      dim3 grid(cdiv(nq, MSDA_TOK), NH, B);
+      msda_sample_kernel<<<grid, MSDA_TOK * 32, 0, st>>>(b.value, b.ol, ldo, b.att_hi, b.att_lo, g, B);
       PN_TRY(check_launch("msda_sample_kernel"));
     }
     {
@@ -261,8 +265,8 @@ int pn_msda_sample(const float* value, const float* ol, float* out, const int* h
   int nq = 0;
   for (int l = 0; l < g.L; ++l) { g.h[l] = h[l]; g.w[l] = wd[l]; g.start[l] = nq; nq += h[l] * wd[l]; }
   g.nq = nq;
-  const long long warps = (long long)B * nq * NH;
-  msda_sample_kernel<<<cdiv(warps, 8), 256, 0, as_stream(stream)>>>(value, ol, NH * num_levels * num_points * 3, out,
+  dim3 grid(cdiv(nq, MSDA_TOK), NH, B);
+  msda_sample_kernel<<<grid, MSDA_TOK * 32, 0, as_stream(stream)>>>(value, ol, NH * num_levels * num_points * 3, out,
                                                                      nullptr, g, B);
   return check_launch("msda_sample_kernel");
 }

