@@ -29,21 +29,58 @@ __device__ __forceinline__ float rna_tf32m(float v) {
 
 // value [B,nq,256] ; ol [B*nq, ldo]: cols [0, 8*L*P*2) offsets ((h,l,p),xy), then 8*L*P attention logits ((h),(l,p))
 // out (hi, lo) [B*nq,256]
-// CTA = MSDA_TOK consecutive tokens (neighbours along x) of ONE head: neighbouring queries sample overlapping
-// taps of the same 128-byte head slice, so most gathers hit L1 instead of L2.
-constexpr int MSDA_TOK = 16;
-__global__ void __launch_bounds__(MSDA_TOK * 32) msda_sample_kernel(const float* __restrict__ value,
-                                                                     const float* __restrict__ ol, int ldo,
-                                                                     float* __restrict__ out_hi,
-                                                                     float* __restrict__ out_lo, const MsdaGeom g,
-                                                                     int B) {
-  const int lane = threadIdx.x & 31;
+// The kernel is instruction-issue bound, not bandwidth bound (the value tensor lives in L2), so the mapping
+// minimises instructions per gathered byte: 8 lanes own one (token, head) and each lane gathers a float4
+// (4 of the 32 head channels); a warp covers 4 consecutive tokens.  Lane j of a group prepares sampling points j
+// and j+8 (softmax weight x bilinear weights, clamped tap addresses) once; the tap loop only broadcasts them
+// inside the 8-lane group and issues 4 x LDG.128 + 16 FFMA per point.
+constexpr int MSDA_TOK = 32;  // tokens per CTA (8 warps x 4)
+struct MsdaPoint {
+  float w00, w01, w10, w11;  // attention weight x bilinear weight (0 for taps outside the map)
+  int r0, r1, x0, x1;        // clamped row offsets (start + y*W) and columns
+};
+__device__ __forceinline__ MsdaPoint msda_point(float aw, float ref_x, float ref_y, float ox, float oy, int W, int H,
+                                                int start) {
+  // pixel coordinates in the sampled level: (ref + off/(W,H)) * (W,H) - 0.5   (grid_sample, align_corners=False)
+  const float x = (ref_x + ox / (float)W) * (float)W - 0.5f;
+  const float y = (ref_y + oy / (float)H) * (float)H - 0.5f;
+  const float xf = floorf(x), yf = floorf(y);
+  const int x0 = (int)xf, y0 = (int)yf;
+  const float lx = x - xf, ly = y - yf;
+  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+  const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+  MsdaPoint p;
+  p.w00 = (xin0 && yin0) ? aw * (1.f - lx) * (1.f - ly) : 0.f;
+  p.w01 = (xin1 && yin0) ? aw * lx * (1.f - ly) : 0.f;
+  p.w10 = (xin0 && yin1) ? aw * (1.f - lx) * ly : 0.f;
+  p.w11 = (xin1 && yin1) ? aw * lx * ly : 0.f;
+  p.x0 = min(max(x0, 0), W - 1);
+  p.x1 = min(max(x0 + 1, 0), W - 1);
+  p.r0 = start + min(max(y0, 0), H - 1) * W;
+  p.r1 = start + min(max(y0 + 1, 0), H - 1) * W;
+  return p;
+}
+__device__ __forceinline__ float seg8_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+}
+__device__ __forceinline__ float seg8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v + __shfl_xor_sync(0xffffffffu, v, 1);
+}
+
+__global__ void __launch_bounds__(256) msda_sample_kernel(const float* __restrict__ value, const float* __restrict__ ol,
+                                                           int ldo, float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                                           const MsdaGeom g, int B) {
+  const int lane = threadIdx.x & 31, sub = lane & 7;
   const int head = blockIdx.y, b = blockIdx.z;
-  const int q = blockIdx.x * MSDA_TOK + (threadIdx.x >> 5);
-  if (q >= g.nq) return;
+  int q = blockIdx.x * MSDA_TOK + (threadIdx.x >> 3);
+  const bool qvalid = q < g.nq;
+  q = qvalid ? q : g.nq - 1;  // keep the whole warp converged for the shuffles; stores are predicated
   const long long tok = (long long)b * g.nq + q;
-  const int LP = g.L * g.P;
-  // reference point of this token (cell centre of its own level, normalised)
+  const int LP = g.L * g.P;   // <= 16
   int ql = 0;
   while (ql + 1 < g.L && q >= g.start[ql + 1]) ++ql;
   const int qi = q - g.start[ql];
@@ -51,57 +88,60 @@ __global__ void __launch_bounds__(MSDA_TOK * 32) msda_sample_kernel(const float*
   const float ref_y = ((float)(qi / g.w[ql]) + 0.5f) / (float)g.h[ql];
 
   const float* row = ol + (size_t)tok * ldo;
-  // lanes [0, LP): one sampling point each
-  float logit = -INFINITY, ox = 0.f, oy = 0.f;
-  if (lane < LP) {
-    logit = __ldg(row + NH * LP * 2 + head * LP + lane);
-    const float2 o = __ldg(reinterpret_cast<const float2*>(row + (head * LP + lane) * 2));
-    ox = o.x; oy = o.y;
+  const int pa = sub, pb = sub + 8;  // the two sampling points this lane prepares
+  float la = -INFINITY, lb = -INFINITY;
+  float2 oa = make_float2(0.f, 0.f), ob = oa;
+  if (pa < LP) {
+    la = __ldg(row + NH * LP * 2 + head * LP + pa);
+    oa = __ldg(reinterpret_cast<const float2*>(row + (head * LP + pa) * 2));
   }
-  float mx = logit;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  float e = (lane < LP) ? __expf(logit - mx) : 0.f;
-  float sum = e;
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-  const float aw = e / sum;
-  // pixel coordinates in the sampled level: (ref + off / (W,H)) * (W,H) - 0.5   (grid_sample, align_corners=False)
-  int lvl = 0, W = 1, H = 1, st = 0;
-  float px = 0.f, py = 0.f;
-  if (lane < LP) {
-    lvl = lane / g.P;
-    W = g.w[lvl]; H = g.h[lvl]; st = g.start[lvl];
-    px = (ref_x + ox / (float)W) * (float)W - 0.5f;
-    py = (ref_y + oy / (float)H) * (float)H - 0.5f;
+  if (pb < LP) {
+    lb = __ldg(row + NH * LP * 2 + head * LP + pb);
+    ob = __ldg(reinterpret_cast<const float2*>(row + (head * LP + pb) * 2));
   }
-  const float* vbase = value + (size_t)b * g.nq * D + head * HD + lane;
-  float acc = 0.f;
+  const float mx = seg8_max(fmaxf(la, lb));
+  const float ea = (pa < LP) ? __expf(la - mx) : 0.f, eb = (pb < LP) ? __expf(lb - mx) : 0.f;
+  const float inv = 1.f / seg8_sum(ea + eb);
+  MsdaPoint A, Bp;
+  {
+    const int lvl = min(pa / g.P, g.L - 1);
+    A = msda_point(ea * inv, ref_x, ref_y, oa.x, oa.y, g.w[lvl], g.h[lvl], g.start[lvl]);
+    const int lvb = min(pb / g.P, g.L - 1);
+    Bp = msda_point(eb * inv, ref_x, ref_y, ob.x, ob.y, g.w[lvb], g.h[lvb], g.start[lvb]);
+  }
+  const float4* vbase = reinterpret_cast<const float4*>(value + (size_t)b * g.nq * D + head * HD) + sub;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
   for (int i = 0; i < LP; ++i) {
-    const float x = __shfl_sync(0xffffffffu, px, i), y = __shfl_sync(0xffffffffu, py, i);
-    const float a = __shfl_sync(0xffffffffu, aw, i);
-    const int w_ = __shfl_sync(0xffffffffu, W, i), h_ = __shfl_sync(0xffffffffu, H, i);
-    const int s_ = __shfl_sync(0xffffffffu, st, i);
-    const float xf = floorf(x), yf = floorf(y);
-    const int x0 = (int)xf, y0 = (int)yf;
-    const float lx = x - xf, ly = y - yf;
-    const float w00 = (1.f - lx) * (1.f - ly), w01 = lx * (1.f - ly), w10 = (1.f - lx) * ly, w11 = lx * ly;
-    const bool xin0 = x0 >= 0 && x0 < w_, xin1 = x0 + 1 >= 0 && x0 + 1 < w_;
-    const bool yin0 = y0 >= 0 && y0 < h_, yin1 = y0 + 1 >= 0 && y0 + 1 < h_;
-    float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
-    if (yin0 && xin0) v00 = __ldg(vbase + (size_t)(s_ + y0 * w_ + x0) * D);
-    if (yin0 && xin1) v01 = __ldg(vbase + (size_t)(s_ + y0 * w_ + x0 + 1) * D);
-    if (yin1 && xin0) v10 = __ldg(vbase + (size_t)(s_ + (y0 + 1) * w_ + x0) * D);
-    if (yin1 && xin1) v11 = __ldg(vbase + (size_t)(s_ + (y0 + 1) * w_ + x0 + 1) * D);
-    acc = fmaf(a, w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11, acc);
+    const bool second = i >= 8;
+    const int src = i & 7;
+    const float w00 = __shfl_sync(0xffffffffu, second ? Bp.w00 : A.w00, src, 8);
+    const float w01 = __shfl_sync(0xffffffffu, second ? Bp.w01 : A.w01, src, 8);
+    const float w10 = __shfl_sync(0xffffffffu, second ? Bp.w10 : A.w10, src, 8);
+    const float w11 = __shfl_sync(0xffffffffu, second ? Bp.w11 : A.w11, src, 8);
+    const int r0 = __shfl_sync(0xffffffffu, second ? Bp.r0 : A.r0, src, 8);
+    const int r1 = __shfl_sync(0xffffffffu, second ? Bp.r1 : A.r1, src, 8);
+    const int x0 = __shfl_sync(0xffffffffu, second ? Bp.x0 : A.x0, src, 8);
+    const int x1 = __shfl_sync(0xffffffffu, second ? Bp.x1 : A.x1, src, 8);
+    const float4 v00 = __ldg(vbase + (size_t)(r0 + x0) * (D / 4));
+    const float4 v01 = __ldg(vbase + (size_t)(r0 + x1) * (D / 4));
+    const float4 v10 = __ldg(vbase + (size_t)(r1 + x0) * (D / 4));
+    const float4 v11 = __ldg(vbase + (size_t)(r1 + x1) * (D / 4));
+    acc.x = fmaf(w00, v00.x, fmaf(w01, v01.x, fmaf(w10, v10.x, fmaf(w11, v11.x, acc.x))));
+    acc.y = fmaf(w00, v00.y, fmaf(w01, v01.y, fmaf(w10, v10.y, fmaf(w11, v11.y, acc.y))));
+    acc.z = fmaf(w00, v00.z, fmaf(w01, v01.z, fmaf(w10, v10.z, fmaf(w11, v11.z, acc.z))));
+    acc.w = fmaf(w00, v00.w, fmaf(w01, v01.w, fmaf(w10, v10.w, fmaf(w11, v11.w, acc.w))));
   }
-  const size_t o = (size_t)tok * D + head * HD + lane;
+  if (!qvalid) return;
+  const size_t o4 = ((size_t)tok * D + head * HD) / 4 + sub;
   if (out_lo) {
-    const float hi = rna_tf32m(acc);
-    out_hi[o] = hi;
-    out_lo[o] = rna_tf32m(acc - hi);
+    float4 hi;
+    hi.x = rna_tf32m(acc.x); hi.y = rna_tf32m(acc.y); hi.z = rna_tf32m(acc.z); hi.w = rna_tf32m(acc.w);
+    reinterpret_cast<float4*>(out_hi)[o4] = hi;
+    reinterpret_cast<float4*>(out_lo)[o4] = make_float4(rna_tf32m(acc.x - hi.x), rna_tf32m(acc.y - hi.y),
+                                                        rna_tf32m(acc.z - hi.z), rna_tf32m(acc.w - hi.w));
   } else {
-    out_hi[o] = acc;
+    reinterpret_cast<float4*>(out_hi)[o4] = acc;
   }
 }
 
@@ -171,8 +211,8 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
                             const int* wd, float* x_out, int B, void* wsp, size_t ws_bytes, pn_stream_t stream) {
   PN_REQUIRE(w && x_in && pos && h && wd && x_out && wsp, PN_ERR_BAD_ARG, "msda_encoder: null argument");
   PN_REQUIRE(w->num_levels >= 1 && w->num_levels <= MSDA_MAX_LEVELS && w->num_points >= 1 &&
-                 w->num_levels * w->num_points <= 32,
-             PN_ERR_UNSUPPORTED, "msda_encoder: levels*points must be <= 32");
+                 w->num_levels * w->num_points <= 16,
+             PN_ERR_UNSUPPORTED, "msda_encoder: levels*points must be <= 16");
   PN_REQUIRE(w->num_layers >= 1 && w->num_layers <= PN_MAX_LAYERS && w->ffn_dims % 32 == 0, PN_ERR_BAD_ARG,
              "msda_encoder: bad layer count / ffn dims");
   cudaStream_t st = as_stream(stream);
@@ -224,7 +264,7 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
     }
     {
       dim3 grid(cdiv(nq, MSDA_TOK), NH, B);
-      msda_sample_kernel<<<grid, MSDA_TOK * 32, 0, st>>>(b.value, b.ol, ldo, b.att_hi, b.att_lo, g, B);
+      msda_sample_kernel<<<grid, 256, 0, st>>>(b.value, b.ol, ldo, b.att_hi, b.att_lo, g, B);
       PN_TRY(check_launch("msda_sample_kernel"));
     }
     {
@@ -258,15 +298,15 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
 int pn_msda_sample(const float* value, const float* ol, float* out, const int* h, const int* wd, int num_levels,
                    int num_points, int B, pn_stream_t stream) {
   PN_REQUIRE(value && ol && out && h && wd, PN_ERR_BAD_ARG, "msda_sample: null argument");
-  PN_REQUIRE(num_levels >= 1 && num_levels <= MSDA_MAX_LEVELS && num_levels * num_points <= 32, PN_ERR_UNSUPPORTED,
-             "msda_sample: levels*points must be <= 32");
+  PN_REQUIRE(num_levels >= 1 && num_levels <= MSDA_MAX_LEVELS && num_levels * num_points <= 16, PN_ERR_UNSUPPORTED,
+             "msda_sample: levels*points must be <= 16");
   MsdaGeom g{};
   g.L = num_levels; g.P = num_points;
   int nq = 0;
   for (int l = 0; l < g.L; ++l) { g.h[l] = h[l]; g.w[l] = wd[l]; g.start[l] = nq; nq += h[l] * wd[l]; }
   g.nq = nq;
   dim3 grid(cdiv(nq, MSDA_TOK), NH, B);
-  msda_sample_kernel<<<grid, MSDA_TOK * 32, 0, as_stream(stream)>>>(value, ol, NH * num_levels * num_points * 3, out,
+  msda_sample_kernel<<<grid, 256, 0, as_stream(stream)>>>(value, ol, NH * num_levels * num_points * 3, out,
                                                                      nullptr, g, B);
   return check_launch("msda_sample_kernel");
 }
