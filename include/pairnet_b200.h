@@ -232,6 +232,12 @@ PN_API size_t pn_msda_encoder_workspace_bytes(int B, int nq, int ffn_dims, int n
 PN_API int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, const float* pos,
                                    const int* h, const int* w_, float* x_out, int B, void* ws, size_t ws_bytes,
                                    pn_stream_t stream);
+/* GroupNorm(groups, 256) (+ReLU) of the pixel decoder's ConvModules; x/y [B,256,HW] (NCHW) or [B,HW,256]
+ * (channels_last = 1); y may alias x. */
+PN_API size_t pn_group_norm_workspace_bytes(int B, int HW, int groups);
+PN_API int pn_group_norm(const float* x, const float* gamma, const float* beta, float* y, int B, int HW,
+                         int groups, int relu, int channels_last, float eps, void* ws, size_t ws_bytes,
+                         pn_stream_t stream);
 /* sampling core only: value [B,nq,256], ol [B*nq, 8*L*P*3] (offsets then attention logits) -> out [B*nq,256] */
 PN_API int pn_msda_sample(const float* value, const float* ol, float* out, const int* h, const int* w_,
                           int num_levels, int num_points, int B, pn_stream_t stream);

@@ -122,6 +122,8 @@ SIGNATURES = {
     "pn_gather_rows": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "pn_msda_encoder_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
     "pn_msda_encoder_forward": (i32, [P(PnMsdaEncoderWeights), vp, vp, P(i32), P(i32), vp, i32, vp, sz, vp]),
+    "pn_group_norm_workspace_bytes": (sz, [i32, i32, i32]),
+    "pn_group_norm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, sz, vp]),
     "pn_msda_sample": (i32, [vp, vp, vp, P(i32), P(i32), i32, i32, i32, vp]),
     "pn_head_workspace_bytes": (sz, [P(PnHeadWeights), P(PnM2FInputs)]),
     "pn_head_forward": (i32, [P(PnHeadWeights), P(PnM2FInputs), P(PnHeadOutputs), vp, sz, vp]),

@@ -93,8 +93,8 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
                          const float* kproj, const float* vproj, int Nk, const uint32_t* bits, int words,
                          const int* rowany, const PnNorm* post_norm, float* xn, LayerScratch& s, cudaStream_t st) {
   const int M = B * Nq;
-  PN_REQUIRE(ffn % (FFN_SPLITS * 32) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
-             FFN_SPLITS * 32);
+  PN_REQUIRE(ffn % (FFN_SPLITS * 64) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
+             FFN_SPLITS * 64);
   // ---- cross attention: q = (x + qpos) Wq^T + bq
   {
     PnLinear q{L.cross_attn.in_proj_w, L.cross_attn.in_proj_b};

@@ -197,9 +197,19 @@ __global__ void __launch_bounds__(256) mha_combine_kernel(const float* __restric
   out[((size_t)b * Nq + qi) * D + c] = den > 0.f ? num / den : 0.f;
 }
 
-static void pick_splits(int B, int Nq, int Nk, int* splits, int* keys_per_split) {
+// split granularity: whole 64-key tiles when the mask is present (bit words are addressed per tile); 16 keys
+// otherwise, so the 100-key self-attention and 200-key relation attention still spread over >100 CTAs.
+static void pick_splits(int B, int Nq, int Nk, bool masked, int* splits, int* keys_per_split) {
   const int qtiles = cdiv(Nq, ATT_THREADS);
   const int base = B * NH * qtiles;
+  if (!masked && Nk <= 512) {
+    int want = cdiv(148, base);
+    int kps = (int)round_up(cdiv(Nk, want), 16);
+    kps = kps < 16 ? 16 : kps;
+    *keys_per_split = kps;
+    *splits = cdiv(Nk, kps);
+    return;
+  }
   const int tiles = cdiv(Nk, ATT_TK);
   int want = cdiv(4 * 148, base);  // ~4 CTAs (16 warps) per SM
   if (want > tiles) want = tiles;
@@ -211,8 +221,10 @@ static void pick_splits(int B, int Nq, int Nk, int* splits, int* keys_per_split)
 }
 
 size_t mha_workspace_bytes(int B, int Nq, int Nk) {
-  int S, kps;
-  pick_splits(B, Nq, Nk, &S, &kps);
+  int S, kps, S2, kps2;
+  pick_splits(B, Nq, Nk, true, &S, &kps);
+  pick_splits(B, Nq, Nk, false, &S2, &kps2);
+  S = S > S2 ? S : S2;
   if (S == 1) return 256;
   size_t o = ((size_t)S * B * Nq * D * sizeof(float) + 255) & ~size_t(255);
   size_t m = ((size_t)S * B * NH * Nq * sizeof(float2) + 255) & ~size_t(255);
@@ -231,7 +243,7 @@ int launch_mha(const MhaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
   k.mask_bits = a.mask_bits; k.mask_words = a.mask_words; k.rowany = a.rowany;
   k.out = a.out; k.B = a.B; k.Nq = a.Nq; k.Nk = a.Nk;
   k.qscale = 0.17677669529663687f * 1.4426950408889634f;
-  pick_splits(a.B, a.Nq, a.Nk, &k.splits, &k.keys_per_split);
+  pick_splits(a.B, a.Nq, a.Nk, a.mask_bits != nullptr, &k.splits, &k.keys_per_split);
   if (k.splits > 1) {
     PN_REQUIRE(ws && ws_bytes >= mha_workspace_bytes(a.B, a.Nq, a.Nk), PN_ERR_WORKSPACE, "mha: workspace too small");
     size_t o = ((size_t)k.splits * a.B * a.Nq * D * sizeof(float) + 255) & ~size_t(255);

@@ -1,7 +1,11 @@
 """UPSTREAM of the hot path (out of scope for hand-written kernels): the mmdet
 ``ResNet`` backbone named by ``configs/mask2former/pairnet.py:9-19``, provided by torchvision's
 ResNet (same architecture and parameter names for ``style='pytorch'``), frozen BN in eval."""
+import copy
+
+import torch
 import torch.nn as nn
+from torch.nn.utils.fusion import fuse_conv_bn_eval
 
 from ..registry import BACKBONES
 
@@ -50,7 +54,45 @@ class ResNet(nn.Module):
     def init_weights(self):
         pass
 
+    # ---- inference fast path: frozen BN folded into the convolutions, channels_last activations -------------
+    def _param_state(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def _fused(self):
+        """A BN-folded, channels_last copy of the stem + stages (rebuilt whenever a weight changes).  The
+        original modules (and their checkpoint-compatible names) stay untouched."""
+        state = self._param_state()
+        cache = self.__dict__.get("_fused_cache")
+        if cache is not None and cache[0] == state:
+            return cache[1]
+        stem = fuse_conv_bn_eval(copy.deepcopy(self.conv1).eval(), copy.deepcopy(self.bn1).eval())
+        stages = []
+        for i in range(1, 5):
+            layer = copy.deepcopy(getattr(self, f"layer{i}")).eval()
+            for blk in layer:
+                for c, b in (("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3")):
+                    setattr(blk, c, fuse_conv_bn_eval(getattr(blk, c), getattr(blk, b)))
+                    setattr(blk, b, nn.Identity())
+                if blk.downsample is not None:
+                    blk.downsample = nn.Sequential(fuse_conv_bn_eval(blk.downsample[0], blk.downsample[1]))
+            stages.append(layer)
+        fused = nn.ModuleList([stem] + stages).to(memory_format=torch.channels_last)
+        for p in fused.parameters():
+            p.requires_grad_(False)
+        self.__dict__["_fused_cache"] = (state, fused)
+        return fused
+
     def forward(self, x):
+        if not self.training and not torch.is_grad_enabled() and x.is_cuda and self.norm_eval:
+            f = self._fused()
+            x = x.contiguous(memory_format=torch.channels_last)
+            x = self.maxpool(torch.relu_(f[0](x)))
+            outs = []
+            for i in range(4):
+                x = f[i + 1](x)
+                if i in self.out_indices:
+                    outs.append(x)
+            return tuple(outs)
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         outs = []
         for i in range(4):

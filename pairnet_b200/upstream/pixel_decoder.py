@@ -39,8 +39,31 @@ class ConvModule(nn.Module):
         self.with_act = act
 
     def forward(self, x):
-        x = self.gn(self.conv(x))
+        x = self.conv(x)
+        if x.is_cuda and not torch.is_grad_enabled() and x.shape[1] == nat.EMBED_DIMS and x.dtype == torch.float32:
+            return self._native_gn(x)
+        x = self.gn(x)
         return F.relu(x, inplace=True) if self.with_act else x
+
+    def _native_gn(self, x):
+        """pn_group_norm: two-pass HBM-bound GroupNorm(+ReLU), NCHW or channels_last storage, in place."""
+        lib = nat.load()
+        B, Cc, H, W = x.shape
+        if x.is_contiguous():
+            cl = 0
+        elif x.is_contiguous(memory_format=torch.channels_last):
+            cl = 1
+        else:
+            x, cl = x.contiguous(), 0
+        need = lib.pn_group_norm_workspace_bytes(B, H * W, self.gn.num_groups)
+        ws = self.__dict__.get("_gn_ws")
+        if ws is None or ws.numel() < need or ws.device != x.device:
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            self.__dict__["_gn_ws"] = ws
+        nat.check(lib.pn_group_norm(x.data_ptr(), self.gn.weight.data_ptr(), self.gn.bias.data_ptr(), x.data_ptr(), B,
+                                    H * W, self.gn.num_groups, int(self.with_act), cl, self.gn.eps, ws.data_ptr(),
+                                    ws.numel(), torch.cuda.current_stream(x.device).cuda_stream), "pn_group_norm")
+        return x
 
 
 class MultiScaleDeformableAttention(nn.Module):

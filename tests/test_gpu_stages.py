@@ -269,3 +269,28 @@ def test_msda_encoder_native_vs_torch():
     # mask_feature passes through cuDNN convs that run TF32 by default on the GPU (upstream plumbing)
     assert rel_err(mf_n, mf_t) < 1e-3
     assert rel_err(mf_n, mf_o) < 5e-3
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("relu", [False, True])
+def test_group_norm_native(channels_last, relu):
+    import ctypes as C
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    B, H, W = 2, 37, 53
+    x = _t((B, 256, H, W), 50, 3.0) + 1.5
+    g, b = _t((256,), 51), _t((256,), 52)
+    ref = F.group_norm(x.double(), 32, g.double(), b.double(), 1e-5)
+    if relu:
+        ref = ref.relu()
+    xc = x.cuda()
+    if channels_last:
+        xc = xc.contiguous(memory_format=torch.channels_last)
+    need = lib.pn_group_norm_workspace_bytes(B, H * W, 32)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    y = torch.empty_like(xc)
+    gc, bc = g.cuda(), b.cuda()  # keep the device tensors alive while their pointers are in use
+    nat.check(lib.pn_group_norm(xc.data_ptr(), gc.data_ptr(), bc.data_ptr(), y.data_ptr(), B, H * W, 32,
+                                int(relu), int(channels_last), 1e-5, ws.data_ptr(), need,
+                                torch.cuda.current_stream().cuda_stream), "gn")
+    assert rel_err(y.cpu(), ref) < 5e-6
