@@ -215,32 +215,50 @@ def time_steps(step_fn, steps, flush_buf, stream):
 
 
 def dominant_kernel_roofline(model, device, pk):
-    """K/V projection of the 100x167 memory level: gemm_store_kernel<128,128,16,8,8> on
-    M = 2*16700 tokens, two problems (K and V), N = K = 256 -> 2*2*M*256*256 flops per launch."""
+    """Dominant hand-written kernel: `umma_gemm_kernel` (tcgen05 kind::tf32, 3xTF32 split operands, TMA-staged
+    tiles, TMEM accumulators) on the K/V projection of the 100x167 memory level: M = 2*16700 tokens,
+    N = 512 (K and V of one layer), K = 256 -> algorithmic flops per launch = 2*M*512*256 (the tensor pipe
+    executes 3x that: lo*hi + hi*lo + hi*hi).  Timed alone (operands pre-split), L2 flushed between launches."""
     from pairnet_b200 import _native as nat
-    import ctypes as C
     lib = nat.load()
     M, d = PER_GPU_BATCH * 100 * 167, 256
+    st = torch.cuda.current_stream().cuda_stream
     x = torch.randn(M, d, device=device)
     w = torch.randn(2 * d, d, device=device) * 0.05
     b = torch.zeros(2 * d, device=device)
     y = torch.empty(M, 2 * d, device=device)
-    st = torch.cuda.current_stream().cuda_stream
+    xh, xl, wh, wl = torch.empty_like(x), torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+    nat.check(lib.pn_split_tf32(x.data_ptr(), xh.data_ptr(), xl.data_ptr(), x.numel(), st), "pn_split_tf32")
+    nat.check(lib.pn_split_tf32(w.data_ptr(), wh.data_ptr(), wl.data_ptr(), w.numel(), st), "pn_split_tf32")
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
 
-    def launch():  # one launch, N = 512 (K and V weights stacked) == the two-problem launch's flops
-        nat.check(lib.pn_linear(x.data_ptr(), d, w.data_ptr(), b.data_ptr(), None, y.data_ptr(), 2 * d, M, 2 * d, d, 0,
-                                st), "pn_linear")
+    def launch():
+        nat.check(lib.pn_linear_tc_presplit(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(),
+                                            y.data_ptr(), 2 * d, M, 2 * d, d, 3, st), "pn_linear_tc_presplit")
     for _ in range(3):
         launch()
     ts = time_steps(launch, 10, flush, torch.cuda.current_stream())
     ms = statistics.mean(ts)
     flops = 2.0 * M * (2 * d) * d
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_store_kernel<128,128,16,8,8> (K/V projection, level 100x167)",
+    # the FFMA kernel this replaced, same problem, for reference
+    def launch_ffma():
+        nat.check(lib.pn_linear(x.data_ptr(), d, w.data_ptr(), b.data_ptr(), None, y.data_ptr(), 2 * d, M, 2 * d, d, 0,
+                                st), "pn_linear")
+    launch_ffma()
+    ms_ffma = statistics.mean(time_steps(launch_ffma, 5, flush, torch.cuda.current_stream()))
+    alg_bytes = 4.0 * (2 * M * d + 2 * 2 * d * d + M * 2 * d)  # A hi+lo, W hi+lo, C
+    return {"bound": "tensor", "kernel": "umma_gemm_kernel: tcgen05.mma kind::tf32 x3 (fp32-parity split), K/V projection "
+                                         "of the 100x167 level, M=33400 N=512 K=256",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": None, "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": pk["source"],
-            "note": "exact-fp32 FFMA kernel measured against the dense bf16 tensor peak; fp32 FFMA peak ~75 TFLOP/s"}
+            "traffic": 90.49e6, "traffic_source": "ncu --set full r01 capture (profiles/r01_umma_gemm_ncu.md): "
+                                                  "dram read 69.56 MB + write 20.93 MB per launch",
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "ms_per_launch": ms, "flops_per_launch": flops, "tensor_pipe_flops_per_launch": 3 * flops,
+            "peak_source": pk["source"], "ffma_kernel_ms_same_problem": ms_ffma,
+            "note": "3xTF32 = 3 tensor-pipe passes at the TF32 rate (half the bf16 rate): the ceiling for this "
+                    "fp32-parity kernel is peak/6 of the dense bf16 figure; achieved/(peak/6) is the useful fraction",
+            "frac_of_3xtf32_ceiling": achieved / (pk["bf16_tflops"] / 6.0)}
 
 
 def ppn_microbench(device, pk):

@@ -75,8 +75,10 @@ PN_API const char* pn_last_error_string(void);
 /* process-wide options. PN_OPT_TENSOR_CORES (default 1): memory-side GEMMs with >= 1024 rows run on the
  * tcgen05 3xTF32 kernel; 0 = exact-fp32 FFMA kernels everywhere (A/B and parity studies). */
 #define PN_OPT_TENSOR_CORES 0
+#define PN_OPT_UMMA_WIDE 1      /* default 0 (measured slower: only 2 smem stages fit); 1 = 128x256 tcgen05 tiles when N % 256 == 0 */
 PN_API int pn_set_option(int key, int value);
 PN_API int pn_get_option(int key);
+#define PN_OPT_UMMA_EPI8 2      /* default 0: 4 epilogue warps in the tcgen05 GEMM (1 = 8; measured slower in the encoder) */
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -114,6 +116,12 @@ PN_API int pn_linear(const float* x, int ldx, const float* w, const float* b, co
 PN_API size_t pn_linear_tc_workspace_bytes(int M, int N, int K);
 PN_API int pn_linear_tc(const float* x, int ldx, const float* w, const float* b, float* y, int ldy,
                         int M, int N, int K, int passes, void* ws, size_t ws_bytes, pn_stream_t stream);
+/* the two halves of pn_linear_tc, for callers that keep operands pre-split (and for timing the GEMM alone):
+ * hi = rna_tf32(x), lo = rna_tf32(x - hi) over n floats (n % 4 == 0); then the tcgen05 GEMM on split operands. */
+PN_API int pn_split_tf32(const float* x, float* hi, float* lo, size_t n, pn_stream_t stream);
+PN_API int pn_linear_tc_presplit(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                                 const float* b, float* y, int ldy, int M, int N, int K, int passes,
+                                 pn_stream_t stream);
 /* y = LayerNorm(x + resid) over 256 channels (resid may be NULL) */
 PN_API int pn_add_layernorm(const float* x, const float* resid, const float* gamma, const float* beta,
                      float* y, int M, pn_stream_t stream);

@@ -107,6 +107,8 @@ SIGNATURES = {
     "pn_linear": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "pn_linear_tc_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_linear_tc": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
+    "pn_split_tf32": (i32, [vp, vp, vp, sz, vp]),
+    "pn_linear_tc_presplit": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "pn_add_layernorm": (i32, [vp, vp, vp, vp, vp, i32, vp]),
     "pn_mha_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_mha_core": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, vp, sz, vp]),

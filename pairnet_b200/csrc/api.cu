@@ -93,8 +93,8 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
                          const float* kproj, const float* vproj, int Nk, const uint32_t* bits, int words,
                          const int* rowany, const PnNorm* post_norm, float* xn, LayerScratch& s, cudaStream_t st) {
   const int M = B * Nq;
-  PN_REQUIRE(ffn % (FFN_SPLITS * 64) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
-             FFN_SPLITS * 64);
+  PN_REQUIRE(ffn % (FFN_SPLITS * 32) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
+             FFN_SPLITS * 32);
   // ---- cross attention: q = (x + qpos) Wq^T + bq
   {
     PnLinear q{L.cross_attn.in_proj_w, L.cross_attn.in_proj_b};
@@ -490,6 +490,16 @@ int pn_linear_tc(const float* x, int ldx, const float* w, const float* b, float*
   PN_TRY(launch_split_tf32(w, wh, wl, (size_t)N * K, st));
   UmmaOperand o{xh, xl, K, wh, wl, K, b, y, ldy, M, N, K};
   return launch_umma_gemm(&o, 1, passes, st);
+}
+
+int pn_split_tf32(const float* x, float* hi, float* lo, size_t n, pn_stream_t stream) {
+  return launch_split_tf32(x, hi, lo, n, as_stream(stream));
+}
+
+int pn_linear_tc_presplit(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* b,
+                          float* y, int ldy, int M, int N, int K, int passes, pn_stream_t stream) {
+  UmmaOperand o{x_hi, x_lo, K, w_hi, w_lo, K, b, y, ldy, M, N, K};
+  return launch_umma_gemm(&o, 1, passes, as_stream(stream));
 }
 
 int pn_add_layernorm(const float* x, const float* resid, const float* gamma, const float* beta, float* y, int M,

@@ -220,139 +220,6 @@ gemm_store_kernel(const __grid_constant__ GemmBatch batch) {
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Query-side GEMMs (M = B*100 rows, K <= 256 per split).  These are latency bound: the weights were evicted
-// from L2 by the memory-side streams of the same forward, so a k-tiled loop pays one HBM round trip per k-tile
-// (measured 11 us per launch regardless of size).  Here the CTA's whole 16 x K and 64 x K operand panels are
-// requested up front with cp.async (4 commit groups of 64 k), so there is ONE exposed round trip and the FMAs of
-// chunk c overlap the arrival of chunks c+1.. .  Thread (ty, tx) owns row ty and columns tx + 16 j (conflict-free
-// 128-bit smem reads; coalesced stores).
-// ------------------------------------------------------------------------------------------------
-constexpr int PANEL_M = 16, PANEL_N = 64, PANEL_K = 256, PANEL_LD = PANEL_K + 4;
-constexpr size_t PANEL_SMEM = (size_t)(PANEL_M + PANEL_N) * PANEL_LD * sizeof(float);
-
-__device__ __forceinline__ void panel_cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-
-constexpr int PANEL_THREADS = 256;
-__global__ void __launch_bounds__(PANEL_THREADS) gemm_panel_kernel(const __grid_constant__ GemmBatch batch) {
-  extern __shared__ __align__(16) float psm[];
-  float* As = psm;
-  float* Ws = psm + PANEL_M * PANEL_LD;
-  int z = blockIdx.z, pi = 0;
-  for (; pi < batch.count - 1; ++pi) {
-    int nz = batch.p[pi].nb * batch.p[pi].splits;
-    if (z < nz) break;
-    z -= nz;
-  }
-  const GemmProb& P = batch.p[pi];
-  const int m0 = blockIdx.y * PANEL_M, n0 = blockIdx.x * PANEL_N;
-  if (m0 >= P.M || n0 >= P.N) return;
-  const int b = z / P.splits, s = z % P.splits;
-  const int kper = P.K / P.splits, k_begin = s * kper;
-  const int nch = kper / 64;
-  const float* A = P.A + (size_t)b * P.sA;
-  const float* W = P.W + (size_t)b * P.sW;
-  float* C = P.C + (size_t)b * P.sC + (size_t)s * P.split_stride;
-  const int tid = threadIdx.x;
-
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c < nch) {
-      for (int i = tid; i < (PANEL_M + PANEL_N) * 16; i += PANEL_THREADS) {
-        const int r = i >> 4, q = i & 15;
-        const int koff = c * 64 + q * 4;
-        if (r < PANEL_M) {
-          float* dst = As + r * PANEL_LD + koff;
-          if (m0 + r < P.M) panel_cp_async16(dst, A + (size_t)(m0 + r) * P.lda + k_begin + koff);
-          else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          float* dst = Ws + (r - PANEL_M) * PANEL_LD + koff;
-          if (n0 + r - PANEL_M < P.N) panel_cp_async16(dst, W + (size_t)(n0 + r - PANEL_M) * P.ldw + k_begin + koff);
-          else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  }
-  // thread (kg, ty, tx): k-group kg (intra-CTA split-K over the two halves of every 64-k chunk), rows ty, ty+8,
-  // columns tx + 16 j -> 2x4 register tile, 6 LDS.128 per 32 FFMA, FFMAs ordered so that consecutive ones are
-  // independent; the two k-groups are summed through shared memory at the end.
-  const int kg = tid >> 7, t7 = tid & 127;
-  const int ty = t7 >> 4, tx = t7 & 15;
-  float acc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c == 0) asm volatile("cp.async.wait_group 3;\n" ::);
-    if (c == 1) asm volatile("cp.async.wait_group 2;\n" ::);
-    if (c == 2) asm volatile("cp.async.wait_group 1;\n" ::);
-    if (c == 3) asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
-    if (c < nch) {
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        const int ko = c * 64 + kg * 32 + k4 * 4;
-        float4 a[2], w[4];
-        a[0] = *reinterpret_cast<const float4*>(As + ty * PANEL_LD + ko);
-        a[1] = *reinterpret_cast<const float4*>(As + (ty + 8) * PANEL_LD + ko);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(Ws + (tx + 16 * j) * PANEL_LD + ko);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
-      }
-    }
-  }
-  // reduce the two k-groups: group 1 parks its 8 partial sums in smem (the A panel is dead by now)
-  __syncthreads();
-  float* red = As;  // [128][8]
-  if (kg == 1) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) red[(i * 4 + j) * 128 + t7] = acc[i][j];
-  }
-  __syncthreads();
-  if (kg == 1) return;
-  const bool epi = (P.splits == 1);
-  const float* resid = (epi && P.resid) ? P.resid + (size_t)b * P.sR : nullptr;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int m = m0 + ty + 8 * i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx + 16 * j;
-      if (m >= P.M || n >= P.N) continue;
-      float x = acc[i][j] + red[(i * 4 + j) * 128 + t7];
-      if (epi) {
-        if (P.bias) x += __ldg(P.bias + n);
-        if (P.relu) x = fmaxf(x, 0.f);
-        if (resid) x += __ldg(resid + (size_t)m * P.ldr + n);
-      }
-      C[(size_t)m * P.ldc + n] = x;
-    }
-  }
-}
-
 GemmProb make_linear(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M,
                      int N, int K, int relu, const float* resid, int ldr) {
   GemmProb p{};
@@ -386,12 +253,7 @@ int launch_gemm(const GemmBatch& batch, cudaStream_t st) {
     nz += batch.p[i].nb * batch.p[i].splits;
   }
   const bool big = maxM >= 1024;
-  bool panel = !big;
-  for (int i = 0; i < batch.count; ++i) {
-    const int kper = batch.p[i].K / (batch.p[i].splits > 0 ? batch.p[i].splits : 1);
-    if (kper > PANEL_K || kper % 64 != 0) panel = false;
-  }
-  const int bk = big ? 16 : (panel ? 64 : 32);
+  const int bk = big ? 16 : 32;
   for (int i = 0; i < batch.count; ++i) {
     PN_TRY(validate(batch.p[i], bk));
     PN_REQUIRE((batch.p[i].ldw & 3) == 0 && ((uintptr_t)batch.p[i].W & 15) == 0, PN_ERR_UNSUPPORTED,
@@ -401,18 +263,6 @@ int launch_gemm(const GemmBatch& batch, cudaStream_t st) {
     dim3 grid(cdiv(maxN, 128), cdiv(maxM, 128), nz);
     gemm_store_kernel<128, 128, 16, 8, 8, false><<<grid, 256, 0, st>>>(batch);
   } else {
-    if (panel) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)PANEL_SMEM);
-        PN_REQUIRE(e == cudaSuccess, (int)e, "gemm_panel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-      }
-      dim3 grid(cdiv(maxN, PANEL_N), cdiv(maxM, PANEL_M), nz);
-      gemm_panel_kernel<<<grid, PANEL_THREADS, PANEL_SMEM, st>>>(batch);
-      return check_launch("gemm_panel_kernel");
-    }
     dim3 grid(cdiv(maxN, 64), cdiv(maxM, 32), nz);
     gemm_store_kernel<32, 64, 32, 4, 4, false><<<grid, 128, 0, st>>>(batch);
   }

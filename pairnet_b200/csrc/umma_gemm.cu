@@ -16,16 +16,22 @@
 namespace pn {
 namespace umma {
 
-constexpr int BM = 128, BN = 128, BK = 32;  // BK fp32 = 128 B = one SWIZZLE_128B row
-constexpr int STAGES = 3;
+constexpr int BM = 128, BK = 32;            // BK fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;                   // kind::tf32: 32 bytes of K per instruction
-constexpr int TILE_BYTES = BM * BK * 4;     // 16 KiB (BM == BN)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES; // a_hi, a_lo, b_hi, b_lo
-constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue
-constexpr int TMEM_COLS = 256;                // two 128-column fp32 accumulators (ping-pong)
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
+// epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each takes half the columns)
 constexpr int BIAS_MAX = 2048;              // per-problem bias staged in smem (epilogue reads it with LDS, not LDG)
-constexpr size_t SMEM_BYTES =
-    (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BIAS_MAX * sizeof(float);
+// BN = 128: 3 stages x 64 KiB, 2 x 128 TMEM columns.  BN = 256 (N % 256 == 0): A tiles are re-read half as often;
+// 2 stages x 96 KiB, 2 x 256 TMEM columns (the whole TMEM).
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN == 128 ? 3 : 2;
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // a_hi, a_lo, b_hi, b_lo
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr size_t SMEM_BYTES =
+      (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BIAS_MAX * sizeof(float);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -96,13 +102,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 128
-__device__ __forceinline__ uint32_t make_idesc() {
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
   uint32_t d = 0;
   d |= 1u << 4;                    // D format: F32
   d |= 2u << 7;                    // A format: TF32
   d |= 2u << 10;                   // B format: TF32
-  d |= (uint32_t)(BN >> 3) << 17;  // N
+  d |= (uint32_t)(bn >> 3) << 17;  // N
   d |= (uint32_t)(BM >> 4) << 24;  // M
   return d;
 }
@@ -132,6 +138,7 @@ struct Params {
 // Tile scheduler: linear tile id -> (problem, m-tile, n-tile), n fastest so that CTAs working at the same time
 // share the A rows in L2.
 struct TileCoord { int p, m0, n0; };
+template <int BN>
 __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
   TileCoord c{0, 0, 0};
 #pragma unroll
@@ -149,7 +156,12 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
 
 // Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM owner), warps2-5 = epilogue.
 // Two 128-column TMEM accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ Params prm) {
+template <int BN, int NUM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(const __grid_constant__ Params prm) {
+  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp0 TMA, warp1 MMA + TMEM alloc, then epilogue warps
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES, OFF_B_HI = 2 * A_TILE_BYTES,
+                OFF_B_LO = 2 * A_TILE_BYTES + Cfg<BN>::B_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -161,7 +173,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= 2) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
-    for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += NUM_THREADS - 64) {
+    for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += NUM_THREADS - 64) {  // epilogue threads
       const int pi = i / BIAS_MAX, n = i % BIAS_MAX;
       float bv = 0.f;
       if (pi < prm.count && prm.p[pi].bias && n < prm.p[pi].N) bv = __ldg(prm.p[pi].bias + n);
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     if (lane == 0) {
       uint32_t it = 0;  // global k-block counter -> smem ring position
       for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(prm, t);
+        const TileCoord tc = tile_coord<BN>(prm, t);
         const Problem& P = prm.p[tc.p];
         const int num_kb = P.K / BK;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -204,13 +216,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-          const uint32_t bytes = (prm.passes == 3) ? STAGE_BYTES : 2 * TILE_BYTES;
+          const uint32_t bytes = (prm.passes == 3) ? STAGE_BYTES : STAGE_BYTES / 2;
           mbar_expect_tx(&full_bar[s], bytes);
-          tma_load_2d(st + 0 * TILE_BYTES, &P.a_hi, &full_bar[s], kb * BK, tc.m0);
-          tma_load_2d(st + 2 * TILE_BYTES, &P.b_hi, &full_bar[s], kb * BK, tc.n0);
+          // B tiles are loaded as BN/128 boxes of 128 rows (the tensor-map box is 32 x 128)
+          tma_load_2d(st + OFF_A_HI, &P.a_hi, &full_bar[s], kb * BK, tc.m0);
+#pragma unroll
+          for (int h = 0; h < BN / 128; ++h)
+            tma_load_2d(st + OFF_B_HI + h * A_TILE_BYTES, &P.b_hi, &full_bar[s], kb * BK, tc.n0 + h * 128);
           if (prm.passes == 3) {
-            tma_load_2d(st + 1 * TILE_BYTES, &P.a_lo, &full_bar[s], kb * BK, tc.m0);
-            tma_load_2d(st + 3 * TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, tc.n0);
+            tma_load_2d(st + OFF_A_LO, &P.a_lo, &full_bar[s], kb * BK, tc.m0);
+#pragma unroll
+            for (int h = 0; h < BN / 128; ++h)
+              tma_load_2d(st + OFF_B_LO + h * A_TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, tc.n0 + h * 128);
           }
         }
       }
@@ -218,10 +235,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   } else if (warp == 1) {
     // ===== MMA issuer (single thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc();
+      const uint32_t idesc = make_idesc(BN);
       uint32_t it = 0, tile_it = 0;
       for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
-        const TileCoord tc = tile_coord(prm, t);
+        const TileCoord tc = tile_coord<BN>(prm, t);
         const int num_kb = prm.p[tc.p].K / BK;
         const uint32_t acc = tile_it & 1;
         mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
@@ -233,8 +250,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           mbar_wait(&full_bar[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(st + 0 * TILE_BYTES), a_lo = make_smem_desc(st + 1 * TILE_BYTES);
-          const uint64_t b_hi = make_smem_desc(st + 2 * TILE_BYTES), b_lo = make_smem_desc(st + 3 * TILE_BYTES);
+          const uint64_t a_hi = make_smem_desc(st + OFF_A_HI), a_lo = make_smem_desc(st + OFF_A_LO);
+          const uint64_t b_hi = make_smem_desc(st + OFF_B_HI), b_lo = make_smem_desc(st + OFF_B_LO);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
@@ -253,11 +270,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 -> TMEM lane quadrant (warp % 4)
+    // ===== epilogue: warps 2..9 -> TMEM lane quadrant (warp % 4), column half ((warp - 2) / 4)
     const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int CH = BN / (NUM_EPI_WARPS / 4);  // columns per epilogue warp
     uint32_t tile_it = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
-      const TileCoord tc = tile_coord(prm, t);
+      const TileCoord tc = tile_coord<BN>(prm, t);
       const Problem& P = prm.p[tc.p];
       const uint32_t acc = tile_it & 1;
       mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
@@ -266,10 +285,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       const int n0 = tc.n0;
       const float* bias_t = bias_s + tc.p * BIAS_MAX + n0;  // n0 + 127 < BIAS_MAX (checked on the host)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * CH; c0 < (chalf + 1) * CH; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + (uint32_t)c0, v);
-        if (c0 + 32 >= BN) {  // last TMEM read of this tile: hand the accumulator back before storing
+        if (c0 + 32 >= (chalf + 1) * CH) {  // last TMEM read of this tile: hand the accumulator back before storing
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0)
@@ -392,7 +411,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     const UmmaOperand& o = ops[i];
     PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || (o.a_lo && o.w_lo)), PN_ERR_BAD_ARG, "umma: null operand");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
-    PN_REQUIRE(cdiv(o.N, BN) * BN <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N, BIAS_MAX);
+    PN_REQUIRE(cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N, BIAS_MAX);
     PN_REQUIRE(o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C must be 16B aligned");
     Problem& p = prm.p[i];
     PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
@@ -407,10 +426,20 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg<128>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)Cfg<128>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_gemm_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)Cfg<256>::SMEM_BYTES);
     PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  bool wide = get_option(OPT_UMMA_WIDE) != 0;
+  for (int i = 0; i < count; ++i) wide = wide && (ops[i].N % 256 == 0);
+  const int BN = wide ? 256 : 128;
   prm.count = count;
   prm.total_tiles = 0;
   for (int i = 0; i < count; ++i) prm.total_tiles += cdiv(ops[i].M, BM) * cdiv(ops[i].N, BN);
@@ -422,7 +451,12 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
-  umma_gemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(prm);
+  if (wide)
+    umma_gemm_kernel<256, 8><<<grid, 64 + 32 * 8, Cfg<256>::SMEM_BYTES, st>>>(prm);
+  else if (get_option(OPT_UMMA_EPI8))
+    umma_gemm_kernel<128, 8><<<grid, 64 + 32 * 8, Cfg<128>::SMEM_BYTES, st>>>(prm);
+  else
+    umma_gemm_kernel<128, 4><<<grid, 64 + 32 * 4, Cfg<128>::SMEM_BYTES, st>>>(prm);
   return check_launch("umma_gemm_kernel");
 }
 
