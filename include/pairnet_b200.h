@@ -79,6 +79,8 @@ PN_API const char* pn_last_error_string(void);
 PN_API int pn_set_option(int key, int value);
 PN_API int pn_get_option(int key);
 #define PN_OPT_UMMA_EPI8 2      /* default 0: 4 epilogue warps in the tcgen05 GEMM (1 = 8; measured slower in the encoder) */
+#define PN_OPT_OVERLAP 3        /* default 1: memory-side K/V projections and the output head run on an internal side
+                                 * stream (fork/join with events; parallel branches under graph capture); 0 = one stream */
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

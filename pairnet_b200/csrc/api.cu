@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 0};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -28,6 +28,37 @@ int check_launch(const char* what) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return (int)e;
   }
+  return 0;
+}
+
+// ---- side stream: independent chains of one forward (memory-side K/V projections, the output head) run on a
+// second stream, forked from / joined to the caller's stream with events, so that under CUDA-graph capture they
+// become parallel branches.  OPT_OVERLAP = 0 keeps everything on the caller's stream.
+struct Side {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev[96];
+  int next = 0;
+  bool ok = false;
+};
+static Side* get_side() {
+  static thread_local Side side;
+  if (!side.ok) {
+    if (cudaStreamCreateWithFlags(&side.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : side.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    side.ok = true;
+  }
+  return &side;
+}
+static cudaEvent_t side_record(Side* sd, cudaStream_t on) {
+  cudaEvent_t e = sd->ev[sd->next];
+  sd->next = (sd->next + 1) % 96;
+  cudaEventRecord(e, on);
+  return e;
+}
+static int side_wait(cudaStream_t who, cudaEvent_t e) {
+  cudaError_t r = cudaStreamWaitEvent(who, e, 0);
+  PN_REQUIRE(r == cudaSuccess, (int)r, "cudaStreamWaitEvent: %s", cudaGetErrorString(r));
   return 0;
 }
 
@@ -91,7 +122,8 @@ static size_t layer_scratch_take(Workspace& ws, LayerScratch& s, int M, int ffn,
 //   kproj/vproj: already projected cross-attention keys/values [B,Nk,256].
 static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos, const float* qpos, int B, int Nq,
                          const float* kproj, const float* vproj, int Nk, const uint32_t* bits, int words,
-                         const int* rowany, const PnNorm* post_norm, float* xn, LayerScratch& s, cudaStream_t st) {
+                         const int* rowany, const PnNorm* post_norm, float* xn, LayerScratch& s, cudaStream_t st,
+                         Side* sd = nullptr, cudaEvent_t* kv_free = nullptr) {
   const int M = B * Nq;
   PN_REQUIRE(ffn % (FFN_SPLITS * 32) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
              FFN_SPLITS * 32);
@@ -101,6 +133,7 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
     PN_TRY(linear1(xpos, D, q, s.qp, D, M, D, D, 0, st));
     MhaArgs a{s.qp, D, kproj, D, vproj, D, bits, words, rowany, s.att, B, Nq, Nk};
     PN_TRY(launch_mha(a, s.mha_ws, s.mha_ws_bytes, st));
+    if (sd && kv_free) *kv_free = side_record(sd, st);  // K/V of this layer may be overwritten from here on
     PnLinear o{L.cross_attn.out_proj_w, L.cross_attn.out_proj_b};
     PN_TRY(linear1(s.att, D, o, s.proj, D, M, D, D, 0, st));
     LnArgs n{};
@@ -176,7 +209,8 @@ constexpr int TC_MIN_ROWS = 1024;  // memory levels with fewer tokens stay on th
 struct M2FBuffers {
   float *X[PN_MAX_LEVELS], *XP[PN_MAX_LEVELS], *Fl[PN_MAX_LEVELS], *pos[PN_MAX_LEVELS];
   float *Xlo[PN_MAX_LEVELS], *XPlo[PN_MAX_LEVELS];  // 3xTF32 low parts (tensor-core K/V projection)
-  float *Whi, *Wlo;                                  // split [Wk;Wv] of the current layer [512,256]
+  float *Whi, *Wlo;                                  // split [Wk;Wv] per layer [nl][512,256]
+  float *K2[2], *V2[2];                              // K/V double buffer (layer i uses set i & 1)
   float *K, *V;
   uint32_t* bits; int* rowany;
   float *x, *xpos, *xn, *e1, *e2, *e;
@@ -192,10 +226,14 @@ static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2F
     b.Fl[l] = ws.take<float>((size_t)p.B * D * p.ldf[l]);
     b.pos[l] = (in && in->pos[l]) ? nullptr : ws.take<float>((size_t)p.hw[l] * D);
   }
-  b.Whi = ws.take<float>((size_t)2 * D * D);
-  b.Wlo = ws.take<float>((size_t)2 * D * D);
-  b.K = ws.take<float>((size_t)p.B * p.maxhw * D);
-  b.V = ws.take<float>((size_t)p.B * p.maxhw * D);
+  b.Whi = ws.take<float>((size_t)p.nl * 2 * D * D);
+  b.Wlo = ws.take<float>((size_t)p.nl * 2 * D * D);
+  for (int t = 0; t < 2; ++t) {
+    b.K2[t] = ws.take<float>((size_t)p.B * p.maxhw * D);
+    b.V2[t] = ws.take<float>((size_t)p.B * p.maxhw * D);
+  }
+  b.K = b.K2[0];
+  b.V = b.V2[0];
   b.bits = ws.take<uint32_t>((size_t)p.M * (p.maxldf / 32));
   b.rowany = ws.take<int>((size_t)p.M);
   b.x = ws.take<float>((size_t)p.M * D);
@@ -207,8 +245,16 @@ static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2F
   layer_scratch_take(ws, b.ls, p.M, p.ffn, p.mha_bytes);
 }
 
+// Deferred output head: when given, cls_pred / mask_pred are produced on the side stream from buffers that
+// outlive this stage's scratch; the caller joins on `done` before reading them.
+struct TailCtx {
+  float *xn, *e1, *e2, *e;   // [M,256] each, caller-owned
+  cudaEvent_t done;
+  bool deferred;
+};
+
 static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2FOutputs* out, Workspace& ws,
-                       cudaStream_t st) {
+                       cudaStream_t st, TailCtx* tail = nullptr) {
   M2FPlan p;
   PN_TRY(m2f_plan(w, in, p));
   PN_REQUIRE(out && out->cls_pred && out->mask_pred, PN_ERR_BAD_ARG, "m2f: null outputs");
@@ -217,6 +263,9 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
   PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "m2f: workspace too small (%zu needed so far, %zu given)", ws.off,
              ws.cap);
   const int HW4 = in->H4 * in->W4;
+  Side* sd = get_option(OPT_OVERLAP) ? get_side() : nullptr;
+  cudaStream_t s2 = sd ? sd->s2 : st;
+  if (tail) { b.xn = tail->xn; b.e1 = tail->e1; b.e2 = tail->e2; b.e = tail->e; tail->deferred = false; }
 
   // ---- row 1 + the linear half of row 2 that does not depend on the queries
   for (int l = 0; l < p.L; ++l) {
@@ -231,6 +280,8 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
                                       st));
   }
+  if (sd) PN_TRY(side_wait(s2, side_record(sd, st)));  // fork: the side stream sees the prepared memories
+  cudaEvent_t kv_free[PN_MAX_LAYERS];
   // ---- learned queries (pairnet_head.py:290-291) and post_norm for the first head call
   PN_TRY(launch_bcast_rows(w->query_feat, w->query_embed, b.x, b.xpos, p.B, p.N, st));
   {
@@ -242,7 +293,33 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     const int l = i % p.L;
     const PnDecoderLayer& Lw = w->layers[i];
     const int words = p.ldf[l] / 32;
-    // forward_head (mask branch only): attn_mask = (mask_embed(post_norm(x)) . resize(F) < 0)
+    float* Kc = b.K2[i & 1];
+    float* Vc = b.V2[i & 1];
+    // ---- memory side (side stream): K/V projections of this layer's level; independent of the queries, so it
+    //      overlaps the query-side chain below.   k = (mem + lvl + pos) Wk^T + bk,  v = (mem + lvl) Wv^T + bv
+    if (sd && i >= 2) PN_TRY(side_wait(s2, kv_free[i - 2]));  // attention of layer i-2 has released this K/V set
+    const int Mk = p.B * p.hw[l];
+    if (get_option(OPT_TENSOR_CORES) && Mk >= TC_MIN_ROWS) {
+      // tcgen05 path: TMA-staged tiles, UMMA kind::tf32 with hi/lo split operands (fp32 parity)
+      float* Whi = b.Whi + (size_t)i * 2 * D * D;
+      float* Wlo = b.Wlo + (size_t)i * 2 * D * D;
+      PN_TRY(launch_split_tf32(Lw.cross_attn.in_proj_w + (size_t)D * D, Whi, Wlo, (size_t)2 * D * D, s2));
+      UmmaOperand o[2] = {
+          {b.XP[l], b.XPlo[l], D, Whi, Wlo, D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk, D, D},
+          {b.X[l], b.Xlo[l], D, Whi + (size_t)D * D, Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, Vc, D, Mk, D,
+           D}};
+      PN_TRY(launch_umma_gemm(o, 2, 3, s2));
+    } else {
+      GemmBatch g{};
+      g.p[0] = make_linear(b.XP[l], D, Lw.cross_attn.in_proj_w + (size_t)D * D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk,
+                           D, D);
+      g.p[1] = make_linear(b.X[l], D, Lw.cross_attn.in_proj_w + (size_t)2 * D * D, Lw.cross_attn.in_proj_b + 2 * D, Vc,
+                           D, Mk, D, D);
+      g.count = 2;
+      PN_TRY(launch_gemm(g, s2));
+    }
+    cudaEvent_t kv_ready = sd ? side_record(sd, s2) : nullptr;
+    // ---- query side: forward_head (mask branch only): attn_mask = (mask_embed(post_norm(x)) . resize(F) < 0)
     PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, st));
     PN_TRY(memset_async(b.rowany, 0, sizeof(int) * p.M, st));
     PN_TRY(launch_gemm_nmajor_maskbits(b.e, b.Fl[l], b.bits, b.rowany, p.B, p.N, p.hw[l], p.ldf[l], st));
@@ -254,39 +331,29 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
                                         p.M, cudaMemcpyDeviceToDevice, st);
       PN_REQUIRE(e == cudaSuccess, (int)e, "mask trace copy: %s", cudaGetErrorString(e));
     }
-    // K/V projections of this layer's memory level: k = (mem + lvl + pos) Wk^T, v = (mem + lvl) Wv^T
-    const int Mk = p.B * p.hw[l];
-    if (get_option(OPT_TENSOR_CORES) && Mk >= TC_MIN_ROWS) {
-      // tcgen05 path: TMA-staged tiles, UMMA kind::tf32 with hi/lo split operands (fp32 parity)
-      PN_TRY(launch_split_tf32(Lw.cross_attn.in_proj_w + (size_t)D * D, b.Whi, b.Wlo, (size_t)2 * D * D, st));
-      UmmaOperand o[2] = {
-          {b.XP[l], b.XPlo[l], D, b.Whi, b.Wlo, D, Lw.cross_attn.in_proj_b + D, b.K, D, Mk, D, D},
-          {b.X[l], b.Xlo[l], D, b.Whi + (size_t)D * D, b.Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, b.V, D,
-           Mk, D, D}};
-      PN_TRY(launch_umma_gemm(o, 2, 3, st));
-    } else {
-      GemmBatch g{};
-      g.p[0] = make_linear(b.XP[l], D, Lw.cross_attn.in_proj_w + (size_t)D * D, Lw.cross_attn.in_proj_b + D, b.K, D,
-                           Mk, D, D);
-      g.p[1] = make_linear(b.X[l], D, Lw.cross_attn.in_proj_w + (size_t)2 * D * D, Lw.cross_attn.in_proj_b + 2 * D,
-                           b.V, D, Mk, D, D);
-      g.count = 2;
-      PN_TRY(launch_gemm(g, st));
-    }
-    PN_TRY(decoder_layer(Lw, p.ffn, b.x, b.xpos, w->query_embed, p.B, p.N, b.K, b.V, p.hw[l], b.bits, words,
-                         b.rowany, &w->post_norm, b.xn, b.ls, st));
+    if (sd) PN_TRY(side_wait(st, kv_ready));  // join: attention needs this layer's K/V
+    PN_TRY(decoder_layer(Lw, p.ffn, b.x, b.xpos, w->query_embed, p.B, p.N, Kc, Vc, p.hw[l], b.bits, words, b.rowany,
+                         &w->post_norm, b.xn, b.ls, st, sd, &kv_free[i]));
     if (out->query_trace) PN_TRY(copy_async(out->query_trace + (size_t)i * p.M * D, b.x, sizeof(float) * p.M * D, st));
   }
-  // ---- last forward_head: cls_pred + full-resolution mask_pred (the only ones that are outputs)
-  PN_TRY(linear1(b.xn, D, w->cls_embed, out->cls_pred, w->num_cls, p.M, w->num_cls, D, 0, st));
-  PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, st));
+  if (out->query_out) PN_TRY(copy_async(out->query_out, b.x, sizeof(float) * p.M * D, st));
+  // ---- last forward_head: cls_pred + full-resolution mask_pred (the only ones that are outputs).  With a
+  //      TailCtx it runs on the side stream, overlapping the PPN / Relation Fusion stages of the caller.
+  const bool defer = sd && tail;
+  cudaStream_t ts = defer ? s2 : st;
+  if (defer) PN_TRY(side_wait(s2, side_record(sd, st)));
+  PN_TRY(linear1(b.xn, D, w->cls_embed, out->cls_pred, w->num_cls, p.M, w->num_cls, D, 0, ts));
+  PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, ts));
   {
     GemmProb g = make_linear(b.e, D, in->mask_features, nullptr, out->mask_pred, HW4, p.N, HW4, D);
     g.ldw = HW4;
     g.nb = p.B; g.sA = (long long)p.N * D; g.sW = (long long)D * HW4; g.sC = (long long)p.N * HW4;
-    PN_TRY(launch_gemm_nmajor_store(g, st));
+    PN_TRY(launch_gemm_nmajor_store(g, ts));
   }
-  if (out->query_out) PN_TRY(copy_async(out->query_out, b.x, sizeof(float) * p.M * D, st));
+  if (defer) {
+    tail->done = side_record(sd, s2);
+    tail->deferred = true;
+  }
   return 0;
 }
 
@@ -589,7 +656,7 @@ size_t pn_head_workspace_bytes(const PnHeadWeights* w, const PnM2FInputs* in) {
   // stage scratch is reused (max), persistent taps are extra
   size_t stage = a > b ? a : b;
   stage = stage > c ? stage : c;
-  const size_t persist = ((size_t)B * N * D * 4 + 255 + (size_t)B * 2 * R * D * 4 + 255) + 1024;
+  const size_t persist = ((size_t)B * N * D * 4 + 255) * 5 + ((size_t)B * 2 * R * D * 4 + 255) + 1024;
   return stage + persist;
 }
 
@@ -608,6 +675,11 @@ int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const PnHeadO
   Workspace P(ws, ws_bytes);
   float* query = out->query_out ? out->query_out : P.take<float>((size_t)B * N * D);
   float* pair = out->pair_feat ? out->pair_feat : P.take<float>((size_t)B * 2 * K * D);
+  TailCtx tail{};
+  tail.xn = P.take<float>((size_t)B * N * D);
+  tail.e1 = P.take<float>((size_t)B * N * D);
+  tail.e2 = P.take<float>((size_t)B * N * D);
+  tail.e = P.take<float>((size_t)B * N * D);
   char* stage = (char*)ws + P.off;
   const size_t stage_bytes = ws_bytes - P.off;
 
@@ -616,7 +688,7 @@ int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const PnHeadO
     mo.query_out = query; mo.cls_pred = out->cls; mo.mask_pred = out->mask;
     mo.query_trace = out->query_trace; mo.mask_trace = out->mask_trace; mo.trace_words = out->trace_words;
     Workspace W(stage, stage_bytes);
-    PN_TRY(m2f_forward(&w->m2f, in, &mo, W, st));
+    PN_TRY(m2f_forward(&w->m2f, in, &mo, W, st, &tail));
   }
   {
     Workspace W(stage, stage_bytes);
@@ -627,6 +699,7 @@ int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const PnHeadO
     Workspace W(stage, stage_bytes);
     PN_TRY(rel_forward(&w->rel, pair, out->rel, out->rel_feat, B, 2 * K, W, st));
   }
+  if (tail.deferred) PN_TRY(side_wait(st, tail.done));  // join: cls / mask are complete
   // row 11 (pairnet_head.py:380-403)
   if (out->sub) PN_TRY(launch_gather_rows(out->cls, out->sub_pos, out->sub, B, N, K, w->m2f.num_cls, st));
   if (out->obj) PN_TRY(launch_gather_rows(out->cls, out->obj_pos, out->obj, B, N, K, w->m2f.num_cls, st));

@@ -139,7 +139,7 @@ int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
                       int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_COUNT = 4 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_COUNT = 4 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);
