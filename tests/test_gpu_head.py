@@ -195,3 +195,60 @@ def test_detector_end_to_end_small_image():
     assert msk["mask"].shape == (2, 100, 64, 80) and msk["sub_seg"].shape == (2, 100, 64, 80)
     assert all(torch.isfinite(v).all() for v in cls.values())
     assert model.bbox_head.last_launch_count > 100
+
+
+@pytest.mark.parametrize("N,R,B,hw4", [(200, 200, 1, (32, 32)), (100, 100, 3, (24, 40)), (50, 30, 2, (16, 24))])
+def test_head_other_query_counts_and_batches(N, R, B, hw4):
+    """CrossHead2 is N-generic (BASELINE config 4 uses 200 queries): build both implementations with
+    num_obj_query=N, num_rel_query=R and compare end to end."""
+    from oracle.head import HeadHyper, OCrossHead2
+    from oracle.make_golden import small_head_inputs
+    from oracle.weights import fixture_state_dict
+    from pairnet_b200.registry import build_head
+    from tests.util import product_head_cfg
+    o = OCrossHead2(HeadHyper(num_obj_query=N, num_rel_query=R, with_pixel_decoder=False))
+    o.load_state_dict(fixture_state_dict(o, 777))
+    o.eval()
+    cfg = product_head_cfg()
+    cfg.update(pixel_decoder=None, num_obj_query=N, num_rel_query=R)
+    p = build_head(cfg)
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.cuda().eval()
+    mf, mems = small_head_inputs(B, hw4, 91)
+    tr = {}
+    with torch.no_grad():
+        ocls, omsk = o.forward_from_memories(mf, mems, trace=tr)
+    taps = {}
+    cls, msk = _run_product(p, mf, mems, taps)
+    assert cls["rel"].shape == (B, R, 56) and cls["importance"].shape == (B, N, N) and cls["sub"].shape == (B, R, 134)
+    assert rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
+    assert rel_err(msk["mask"], omsk["mask"]) < RTOL_LOGITS
+    assert rel_err(cls["importance"], ocls["importance"]) < RTOL_LOGITS
+    tol = RTOL_LOGITS * float(ocls["importance"].abs().max())
+    swapped = check_topk_tie_aware(ocls["importance"], taps["sub_pos"], taps["obj_pos"], tr["sub_pos"], tr["obj_pos"], tol)
+    if swapped == 0:
+        assert rel_err(cls["rel"], ocls["rel"]) < RTOL_LOGITS
+
+
+def test_overlap_and_tensor_core_options_are_result_neutral(heads):
+    """Side-stream overlap must be bit-neutral; tensor cores (3xTF32) vs the exact-FFMA path agree to fp32 noise."""
+    from oracle.make_golden import small_head_inputs
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    _, p = heads
+    mf, mems = _full_size_inputs(1, 55)
+    try:
+        base_cls, base_msk = _run_product(p, mf, mems)
+        lib.pn_set_option(3, 0)  # PN_OPT_OVERLAP off
+        c1, m1 = _run_product(p, mf, mems)
+        for k in base_cls:
+            assert torch.equal(base_cls[k], c1[k]), k
+        assert torch.equal(base_msk["mask"], m1["mask"])
+        lib.pn_set_option(0, 0)  # PN_OPT_TENSOR_CORES off -> exact FFMA everywhere
+        c2, m2 = _run_product(p, mf, mems)
+        assert rel_err(c2["cls"], base_cls["cls"]) < 1e-4
+        assert rel_err(m2["mask"], base_msk["mask"]) < 1e-4
+        assert rel_err(c2["importance"], base_cls["importance"]) < 1e-3
+    finally:
+        lib.pn_set_option(3, 1)
+        lib.pn_set_option(0, 1)
