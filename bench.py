@@ -255,8 +255,8 @@ def dominant_kernel_roofline(model, device, pk):
     return {"bound": "tensor", "kernel": "umma_gemm_kernel: tcgen05.mma kind::tf32 x3 (fp32-parity split), K/V projection "
                                          "of the 100x167 level, M=33400 N=512 K=256",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": 90.49e6, "traffic_source": "ncu --set full r01 capture (profiles/r01_umma_gemm_ncu.md): "
-                                                  "dram read 69.56 MB + write 20.93 MB per launch",
+            "traffic": 87.48e6, "traffic_source": "ncu --set full r01 capture (profiles/r01_umma_gemm_ncu.md): "
+                                                  "dram read 69.59 MB + write 17.90 MB per launch",
             "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": flops, "tensor_pipe_flops_per_launch": 3 * flops,
             "peak_source": pk["source"], "ffma_kernel_ms_same_problem": ms_ffma,
