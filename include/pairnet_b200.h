@@ -81,6 +81,7 @@ PN_API int pn_get_option(int key);
 #define PN_OPT_UMMA_EPI8 2      /* default 0: 4 epilogue warps in the tcgen05 GEMM (1 = 8; measured slower in the encoder) */
 #define PN_OPT_OVERLAP 3        /* default 1: memory-side K/V projections and the output head run on an internal side
                                  * stream (fork/join with events; parallel branches under graph capture); 0 = one stream */
+#define PN_OPT_FA_TC 4          /* default 1: masked cross-attention of levels with >= 1024 tokens on tcgen05 (0 = FFMA) */
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -135,6 +136,14 @@ PN_API size_t pn_mha_workspace_bytes(int B, int Nq, int Nk);
 PN_API int pn_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
                 const uint32_t* mask_bits, int mask_words, const int* rowany,
                 float* out, int B, int Nq, int Nk, void* ws, size_t ws_bytes, pn_stream_t stream);
+
+/* Tensor-core variant of pn_mha_core (fa_umma.cu): QK^T and PV on tcgen05 (3xTF32 operands, P staged through
+ * TMEM); same arguments, dense q/k/v with row stride 256.  Used by the M2F decoder for memory levels with
+ * >= 1024 tokens (there the K/V projection emits the split / transposed operands directly). */
+PN_API size_t pn_mha_core_tc_workspace_bytes(int B, int Nq, int Nk);
+PN_API int pn_mha_core_tc(const float* q, const float* k, const float* v, const uint32_t* mask_bits,
+                          int mask_words, const int* rowany, float* out, int B, int Nq, int Nk, void* ws,
+                          size_t ws_bytes, pn_stream_t stream);
 
 /* ------------------------------------------------------------------ rows 3 (+1,2): M2F decoder
  * replaces pairnet_head.py:262-320 minus the pixel decoder call. */

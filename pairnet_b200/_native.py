@@ -112,6 +112,8 @@ SIGNATURES = {
     "pn_add_layernorm": (i32, [vp, vp, vp, vp, vp, i32, vp]),
     "pn_mha_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_mha_core": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, vp, sz, vp]),
+    "pn_mha_core_tc_workspace_bytes": (sz, [i32, i32, i32]),
+    "pn_mha_core_tc": (i32, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, vp, sz, vp]),
     "pn_m2f_decoder_workspace_bytes": (sz, [P(PnM2FWeights), P(PnM2FInputs)]),
     "pn_m2f_decoder_forward": (i32, [P(PnM2FWeights), P(PnM2FInputs), P(PnM2FOutputs), vp, sz, vp]),
     "pn_ppn_workspace_bytes": (sz, [i32, i32, i32, i32]),

@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 0, 0, 0};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -90,6 +90,12 @@ static int mlp3(const float* x, const PnMlp3& m, float* t1, float* t2, float* y,
   return linear1(t2, D, m.l[2], y, D, M, D, D, 0, st);
 }
 
+// K / V^T of one layer in the split form the tensor-core attention consumes
+struct FaKV {
+  const float *k_hi, *k_lo, *vt_hi, *vt_lo;
+  int ldv;
+};
+
 struct LayerScratch {
   float *x1, *x2;       // [M,256]
   float *qp;            // [M,256] projected cross-attn queries
@@ -123,7 +129,7 @@ static size_t layer_scratch_take(Workspace& ws, LayerScratch& s, int M, int ffn,
 static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos, const float* qpos, int B, int Nq,
                          const float* kproj, const float* vproj, int Nk, const uint32_t* bits, int words,
                          const int* rowany, const PnNorm* post_norm, float* xn, LayerScratch& s, cudaStream_t st,
-                         Side* sd = nullptr, cudaEvent_t* kv_free = nullptr) {
+                         Side* sd = nullptr, cudaEvent_t* kv_free = nullptr, const FaKV* fa = nullptr) {
   const int M = B * Nq;
   PN_REQUIRE(ffn % (FFN_SPLITS * 32) == 0, PN_ERR_UNSUPPORTED, "ffn_dims=%d must be a multiple of %d", ffn,
              FFN_SPLITS * 32);
@@ -131,8 +137,17 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
   {
     PnLinear q{L.cross_attn.in_proj_w, L.cross_attn.in_proj_b};
     PN_TRY(linear1(xpos, D, q, s.qp, D, M, D, D, 0, st));
-    MhaArgs a{s.qp, D, kproj, D, vproj, D, bits, words, rowany, s.att, B, Nq, Nk};
-    PN_TRY(launch_mha(a, s.mha_ws, s.mha_ws_bytes, st));
+    if (fa) {
+      // tcgen05 flash attention: q scaled + split hi/lo (s.qk doubles as the two [M,256] halves)
+      float* q_hi = s.qk;
+      float* q_lo = s.qk + (size_t)M * D;
+      PN_TRY(launch_split_tf32_scaled(s.qp, q_hi, q_lo, (size_t)M * D, ATTN_QSCALE, st));
+      FaArgs a{q_hi, q_lo, fa->k_hi, fa->k_lo, fa->vt_hi, fa->vt_lo, fa->ldv, bits, words, rowany, s.att, B, Nq, Nk};
+      PN_TRY(launch_fa_umma(a, s.mha_ws, s.mha_ws_bytes, st));
+    } else {
+      MhaArgs a{s.qp, D, kproj, D, vproj, D, bits, words, rowany, s.att, B, Nq, Nk};
+      PN_TRY(launch_mha(a, s.mha_ws, s.mha_ws_bytes, st));
+    }
     if (sd && kv_free) *kv_free = side_record(sd, st);  // K/V of this layer may be overwritten from here on
     PnLinear o{L.cross_attn.out_proj_w, L.cross_attn.out_proj_b};
     PN_TRY(linear1(s.att, D, o, s.proj, D, M, D, D, 0, st));
@@ -201,6 +216,8 @@ static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
     p.maxldf = p.ldf[l] > p.maxldf ? p.ldf[l] : p.maxldf;
     size_t mb = mha_workspace_bytes(p.B, p.N, p.hw[l]);
     p.mha_bytes = mb > p.mha_bytes ? mb : p.mha_bytes;
+    mb = fa_workspace_bytes(p.B, p.N, p.hw[l]);
+    p.mha_bytes = mb > p.mha_bytes ? mb : p.mha_bytes;
   }
   return 0;
 }
@@ -211,6 +228,7 @@ struct M2FBuffers {
   float *Xlo[PN_MAX_LEVELS], *XPlo[PN_MAX_LEVELS];  // 3xTF32 low parts (tensor-core K/V projection)
   float *Whi, *Wlo;                                  // split [Wk;Wv] per layer [nl][512,256]
   float *K2[2], *V2[2];                              // K/V double buffer (layer i uses set i & 1)
+  float *Klo2[2], *Vlo2[2];                          // tensor-core attention: K lo, and V2/Vlo2 hold V^T hi/lo
   float *K, *V;
   uint32_t* bits; int* rowany;
   float *x, *xpos, *xn, *e1, *e2, *e;
@@ -230,7 +248,9 @@ static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2F
   b.Wlo = ws.take<float>((size_t)p.nl * 2 * D * D);
   for (int t = 0; t < 2; ++t) {
     b.K2[t] = ws.take<float>((size_t)p.B * p.maxhw * D);
-    b.V2[t] = ws.take<float>((size_t)p.B * p.maxhw * D);
+    b.V2[t] = ws.take<float>((size_t)p.B * (p.maxhw + 4) * D);
+    b.Klo2[t] = ws.take<float>((size_t)p.B * p.maxhw * D);
+    b.Vlo2[t] = ws.take<float>((size_t)p.B * (p.maxhw + 4) * D);
   }
   b.K = b.K2[0];
   b.V = b.V2[0];
@@ -299,7 +319,10 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     //      overlaps the query-side chain below.   k = (mem + lvl + pos) Wk^T + bk,  v = (mem + lvl) Wv^T + bv
     if (sd && i >= 2) PN_TRY(side_wait(s2, kv_free[i - 2]));  // attention of layer i-2 has released this K/V set
     const int Mk = p.B * p.hw[l];
-    if (get_option(OPT_TENSOR_CORES) && Mk >= TC_MIN_ROWS) {
+    const bool tc = get_option(OPT_TENSOR_CORES) && Mk >= TC_MIN_ROWS;
+    const bool fa_tc = tc && get_option(OPT_FA_TC);
+    FaKV fa{Kc, b.Klo2[i & 1], Vc, b.Vlo2[i & 1], (int)round_up(p.hw[l], 4)};
+    if (tc) {
       // tcgen05 path: TMA-staged tiles, UMMA kind::tf32 with hi/lo split operands (fp32 parity)
       float* Whi = b.Whi + (size_t)i * 2 * D * D;
       float* Wlo = b.Wlo + (size_t)i * 2 * D * D;
@@ -308,6 +331,12 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
           {b.XP[l], b.XPlo[l], D, Whi, Wlo, D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk, D, D},
           {b.X[l], b.Xlo[l], D, Whi + (size_t)D * D, Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, Vc, D, Mk, D,
            D}};
+      if (fa_tc) {  // emit K split hi/lo and V transposed per image (keys contiguous) + split, for fa_umma_kernel
+        o[0].C_lo = b.Klo2[i & 1];
+        o[1].C_lo = b.Vlo2[i & 1];
+        o[1].t_rows = p.hw[l];
+        o[1].ldc = fa.ldv;
+      }
       PN_TRY(launch_umma_gemm(o, 2, 3, s2));
     } else {
       GemmBatch g{};
@@ -333,7 +362,7 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     }
     if (sd) PN_TRY(side_wait(st, kv_ready));  // join: attention needs this layer's K/V
     PN_TRY(decoder_layer(Lw, p.ffn, b.x, b.xpos, w->query_embed, p.B, p.N, Kc, Vc, p.hw[l], b.bits, words, b.rowany,
-                         &w->post_norm, b.xn, b.ls, st, sd, &kv_free[i]));
+                         &w->post_norm, b.xn, b.ls, st, sd, &kv_free[i], fa_tc ? &fa : nullptr));
     if (out->query_trace) PN_TRY(copy_async(out->query_trace + (size_t)i * p.M * D, b.x, sizeof(float) * p.M * D, st));
   }
   if (out->query_out) PN_TRY(copy_async(out->query_out, b.x, sizeof(float) * p.M * D, st));
@@ -583,6 +612,36 @@ int pn_mha_core(const float* q, int ldq, const float* k, int ldk, const float* v
                 pn_stream_t stream) {
   MhaArgs a{q, ldq, k, ldk, v, ldv, mask_bits, mask_words, rowany, out, B, Nq, Nk};
   return launch_mha(a, ws, ws_bytes, as_stream(stream));
+}
+
+static void fa_test_take(Workspace& ws, int B, int Nq, int Nk, float** p) {
+  const int ldv = (int)round_up(Nk, 4);
+  p[0] = ws.take<float>((size_t)B * Nq * D); p[1] = ws.take<float>((size_t)B * Nq * D);
+  p[2] = ws.take<float>((size_t)B * Nk * D); p[3] = ws.take<float>((size_t)B * Nk * D);
+  p[4] = ws.take<float>((size_t)B * D * ldv); p[5] = ws.take<float>((size_t)B * D * ldv);
+  p[6] = reinterpret_cast<float*>(ws.take<char>(fa_workspace_bytes(B, Nq, Nk)));
+}
+size_t pn_mha_core_tc_workspace_bytes(int B, int Nq, int Nk) {
+  Workspace ws(nullptr, 0);
+  float* p[7];
+  fa_test_take(ws, B, Nq, Nk, p);
+  return ws.off + 256;
+}
+int pn_mha_core_tc(const float* q, const float* k, const float* v, const uint32_t* mask_bits, int mask_words,
+                   const int* rowany, float* out, int B, int Nq, int Nk, void* wsp, size_t ws_bytes,
+                   pn_stream_t stream) {
+  PN_REQUIRE(q && k && v && out && wsp, PN_ERR_BAD_ARG, "mha_core_tc: null pointer");
+  Workspace ws(wsp, ws_bytes);
+  float* p[7];
+  fa_test_take(ws, B, Nq, Nk, p);
+  PN_REQUIRE(ws.ok(), PN_ERR_WORKSPACE, "mha_core_tc: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int ldv = (int)round_up(Nk, 4);
+  PN_TRY(launch_split_tf32_scaled(q, p[0], p[1], (size_t)B * Nq * D, ATTN_QSCALE, st));
+  PN_TRY(launch_split_tf32(k, p[2], p[3], (size_t)B * Nk * D, st));
+  PN_TRY(launch_split_transpose(v, p[4], p[5], B, Nk, ldv, st));
+  FaArgs a{p[0], p[1], p[2], p[3], p[4], p[5], ldv, mask_bits, mask_words, rowany, out, B, Nq, Nk};
+  return launch_fa_umma(a, p[6], fa_workspace_bytes(B, Nq, Nk), st);
 }
 
 size_t pn_m2f_decoder_workspace_bytes(const PnM2FWeights* w, const PnM2FInputs* in) {

@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(256) mha_combine_kernel(const float* __restric
 
 // split granularity: whole 64-key tiles when the mask is present (bit words are addressed per tile); 16 keys
 // otherwise, so the 100-key self-attention and 200-key relation attention still spread over >100 CTAs.
+int launch_mha_combine(const float* opart, const float2* ml, float* out, int B, int Nq, int S, cudaStream_t st) {
+  mha_combine_kernel<<<B * Nq, 256, 0, st>>>(opart, ml, out, B, Nq, S);
+  return check_launch("mha_combine_kernel");
+}
+
 static void pick_splits(int B, int Nq, int Nk, bool masked, int* splits, int* keys_per_split) {
   const int qtiles = cdiv(Nq, ATT_THREADS);
   const int base = B * NH * qtiles;

@@ -96,6 +96,7 @@ struct UmmaOperand {
   int M, N, K;
   float* C_lo;   // optional: emit the result pre-split (C = hi, C_lo = lo) for a chained 3xTF32 GEMM
   int relu;
+  int t_rows;    // > 0: transposed store C[(m / t_rows) * N + n][m % t_rows] with row pitch ldc (V^T per image)
 };
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st);
@@ -135,11 +136,30 @@ struct MhaArgs {
 size_t mha_workspace_bytes(int B, int Nq, int Nk);
 int launch_mha(const MhaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int launch_mha_combine(const float* opart, const float2* ml, float* out, int B, int Nq, int S, cudaStream_t st);
+
+// tensor-core flash attention (fa_umma.cu): operands pre-split hi/lo; q pre-scaled by (1/sqrt(32))*log2(e)
+struct FaArgs {
+  const float* q_hi; const float* q_lo;      // [B*Nq, 256]
+  const float* k_hi; const float* k_lo;      // [B*Nk, 256]
+  const float* vt_hi; const float* vt_lo;    // [B*256, ldv]  V^T per image (row = head*32 + dim, col = key)
+  int ldv;
+  const uint32_t* mask_bits; int mask_words;
+  const int* rowany;
+  float* out;                                // [B,Nq,256]
+  int B, Nq, Nk;
+};
+size_t fa_workspace_bytes(int B, int Nq, int Nk);
+int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_split_tf32_scaled(const float* x, float* hi, float* lo, size_t n, float scale, cudaStream_t st);
+int launch_split_transpose(const float* v, float* vt_hi, float* vt_lo, int B, int Nk, int ldv, cudaStream_t st);
+constexpr float ATTN_QSCALE = 0.17677669529663687f * 1.4426950408889634f;  // (1/sqrt(32)) * log2(e)
+
 int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
                       int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_COUNT = 4 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_COUNT = 8 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);

@@ -9,15 +9,12 @@
 // the accumulator receives lo*hi + hi*lo + hi*hi, i.e. all product bits down to ~2^-22 relative, so the
 // result matches an fp32 FFMA GEMM to ~1e-6 while running on the tensor pipe.  `passes = 1` (hi*hi only)
 // is plain TF32.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace pn {
 namespace umma {
 
 constexpr int BM = 128, BK = 32;            // BK fp32 = 128 B = one SWIZZLE_128B row
-constexpr int UMMA_K = 8;                   // kind::tf32: 32 bytes of K per instruction
 constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
 // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each takes half the columns)
 constexpr int BIAS_MAX = 2048;              // per-problem bias staged in smem (epilogue reads it with LDS, not LDG)
@@ -33,92 +30,6 @@ struct Cfg {
       (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BIAS_MAX * sizeof(float);
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major operand tile [rows][128 B], SWIZZLE_128B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
-  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-  return d;
-}
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
-  uint32_t d = 0;
-  d |= 1u << 4;                    // D format: F32
-  d |= 2u << 7;                    // A format: TF32
-  d |= 2u << 10;                   // B format: TF32
-  d |= (uint32_t)(bn >> 3) << 17;  // N
-  d |= (uint32_t)(BM >> 4) << 24;  // M
-  return d;
-}
-
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
 struct Problem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;  // A [M,K], W [N,K]; box 32 x 128, SWIZZLE_128B
   const float* bias;
@@ -126,6 +37,7 @@ struct Problem {
   float* C_lo;  // non-null: write the result pre-split for a following 3xTF32 GEMM (C = hi, C_lo = lo)
   int M, N, K, ldc;
   int relu;
+  int t_rows;   // > 0: transposed store  C[(m / t_rows) * N + n][m % t_rows]  (row pitch ldc), e.g. V^T per image
 };
 constexpr int MAX_PROBLEMS = 2;
 struct Params {
@@ -294,7 +206,27 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
         }
-        if (row < P.M && n0 + c0 < P.N) {
+        if (row < P.M && n0 + c0 < P.N && P.t_rows > 0) {
+          // transposed store: lanes hold consecutive rows -> each column is one coalesced 128-byte store
+          const int bi = row / P.t_rows, r = row - bi * P.t_rows;
+          const float* bias_c = bias_t + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < P.N) {
+              float x = __uint_as_float(v[j]) + bias_c[j];
+              x = P.relu ? fmaxf(x, 0.f) : x;
+              const size_t o = ((size_t)bi * P.N + n) * P.ldc + r;
+              if (P.C_lo) {
+                const float h = rna_tf32(x);
+                P.C[o] = h;
+                P.C_lo[o] = rna_tf32(x - h);
+              } else {
+                P.C[o] = x;
+              }
+            }
+          }
+        } else if (row < P.M && n0 + c0 < P.N) {
           float* dst = P.C + (size_t)row * P.ldc + n0 + c0;
           float* dlo = P.C_lo ? P.C_lo + (size_t)row * P.ldc + n0 + c0 : nullptr;
 #pragma unroll
@@ -344,9 +276,10 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
 
 // ---- hi/lo split (round-to-nearest tf32) ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
-                                                          float* __restrict__ lo, size_t n4) {
+                                                          float* __restrict__ lo, size_t n4, float scale) {
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     float4 h, l;
     h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
     l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
@@ -372,14 +305,15 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major fp32 matrix [rows, cols] with leading dimension ld (elements); box = 32 cols x 128 rows
-static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld) {
+int make_tmap_2d(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_cols,
+                 int box_rows) {
   EncodeTiledFn fn = encode_fn();
   PN_REQUIRE(fn, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   PN_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, PN_ERR_UNSUPPORTED, "umma: operand must be 16B aligned");
+  PN_REQUIRE(box_cols * 4 == 128 && box_rows >= 1 && box_rows <= 256, PN_ERR_BAD_ARG, "umma: bad TMA box");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -387,16 +321,54 @@ static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int 
   PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
+static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld) {
+  return make_tmap_2d(map, ptr, rows, cols, ld, BK, BM);
+}
 
 }  // namespace umma
 
+// v [B,Nk,256] -> V^T per image: vt[(b*256 + c) * ldv + key] split hi/lo (32x32 smem transpose tiles)
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ v, float* __restrict__ vt_hi,
+                                                               float* __restrict__ vt_lo, int Nk, int ldv) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int key = k0 + ty + r * 8;
+    tile[ty + r * 8][tx] = key < Nk ? __ldg(v + ((size_t)b * Nk + key) * D + c0 + tx) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + r * 8, key = k0 + tx;
+    if (key < Nk) {
+      const float x = tile[tx][ty + r * 8];
+      const float h = umma::rna_tf32(x);
+      const size_t o = ((size_t)b * D + c) * ldv + key;
+      vt_hi[o] = h;
+      vt_lo[o] = umma::rna_tf32(x - h);
+    }
+  }
+}
+
+int launch_split_transpose(const float* v, float* vt_hi, float* vt_lo, int B, int Nk, int ldv, cudaStream_t st) {
+  dim3 grid(cdiv(Nk, 32), D / 32, B);
+  split_transpose_kernel<<<grid, 256, 0, st>>>(v, vt_hi, vt_lo, Nk, ldv);
+  return check_launch("split_transpose_kernel");
+}
+
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  return launch_split_tf32_scaled(x, hi, lo, n, 1.0f, st);
+}
+
+int launch_split_tf32_scaled(const float* x, float* hi, float* lo, size_t n, float scale, cudaStream_t st) {
   PN_REQUIRE(x && hi && lo && n % 4 == 0, PN_ERR_BAD_ARG, "split_tf32: bad args");
   PN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, PN_ERR_UNSUPPORTED, "split_tf32: alignment");
   const size_t n4 = n / 4;
   int blocks = (int)((n4 + 255) / 256);
   blocks = blocks > 148 * 16 ? 148 * 16 : (blocks < 1 ? 1 : blocks);
-  umma::split_tf32_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n4);
+  umma::split_tf32_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n4, scale);
   return check_launch("split_tf32_kernel");
 }
 
@@ -412,14 +384,15 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || (o.a_lo && o.w_lo)), PN_ERR_BAD_ARG, "umma: null operand");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
     PN_REQUIRE(cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N, BIAS_MAX);
-    PN_REQUIRE(o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C must be 16B aligned");
+    PN_REQUIRE(o.t_rows > 0 || (o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0), PN_ERR_UNSUPPORTED,
+               "umma: C must be 16B aligned");
     Problem& p = prm.p[i];
     PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
     PN_TRY(make_map(&p.a_lo, passes == 3 ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
-    p.C_lo = o.C_lo; p.relu = o.relu;
+    p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows;
     PN_REQUIRE(!o.C_lo || ((uintptr_t)o.C_lo & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C_lo must be 16B aligned");
     maxM = o.M > maxM ? o.M : maxM;
     maxN = o.N > maxN ? o.N : maxN;

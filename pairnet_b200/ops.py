@@ -123,6 +123,23 @@ def mha_core(q, k, v, mask_bits=None, rowany=None):
     return out
 
 
+def mha_core_tc(q, k, v, mask_bits=None, rowany=None):
+    """tcgen05 flash attention (3xTF32): q [B,Nq,256], k/v [B,Nk,256] (already projected) -> [B,Nq,256]."""
+    q, k, v = _f32(q), _f32(k), _f32(v)
+    B, Nq, _ = q.shape
+    Nk = k.shape[1]
+    lib = nat.load()
+    need = lib.pn_mha_core_tc_workspace_bytes(B, Nq, Nk)
+    ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+    out = torch.empty((B, Nq, 256), dtype=torch.float32, device=q.device)
+    nat.check(lib.pn_mha_core_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                 mask_bits.data_ptr() if mask_bits is not None else None,
+                                 mask_bits.shape[-1] if mask_bits is not None else 0,
+                                 rowany.data_ptr() if rowany is not None else None, out.data_ptr(), B, Nq, Nk,
+                                 ws.data_ptr(), need, _stream(q)), "pn_mha_core_tc")
+    return out
+
+
 def _conv_struct(conv):
     cv = nat.PnConvTiny()
     cv.mid_channels = conv.conv_layers[0][0].out_channels

@@ -117,6 +117,38 @@ def test_mha_core_masked_with_fully_blocked_rows(Nk):
     assert rel_err(got, _mha_ref(q, k, v, blocked)) < 5e-6
 
 
+@pytest.mark.parametrize("Nq,Nk", [(100, 128), (100, 1050), (100, 4200), (130, 333), (200, 2100)])
+def test_mha_core_tc_unmasked(Nq, Nk):
+    """tcgen05 flash attention (QK^T and PV on tensor cores, P through TMEM) vs fp64 math."""
+    from pairnet_b200 import ops
+    q, k, v = _t((2, Nq, 256), 13), _t((2, Nk, 256), 14), _t((2, Nk, 256), 15)
+    got = ops.mha_core_tc(q.cuda(), k.cuda(), v.cuda()).cpu()
+    assert rel_err(got, _mha_ref(q, k, v)) < 1e-5
+
+
+@pytest.mark.parametrize("Nk", [200, 1050, 4200])
+def test_mha_core_tc_masked_with_fully_blocked_rows(Nk):
+    from pairnet_b200 import ops
+    B, Nq = 2, 100
+    q, k, v = _t((B, Nq, 256), 16, 2.0), _t((B, Nk, 256), 17), _t((B, Nk, 256), 18)
+    rng = np.random.default_rng(Nk)
+    blocked = torch.from_numpy(rng.random((B, Nq, Nk)) < 0.6)
+    blocked[0, 3] = True
+    blocked[1, 99] = True
+    blocked[0, 5] = True
+    blocked[0, 5, Nk - 1] = False
+    blocked[1, 7, 64:] = True
+    blocked[1, 8, :Nk - 130] = True  # open keys only in the last two tiles
+    words = (Nk + 63) // 64 * 2
+    padded = torch.ones((B, Nq, words * 32), dtype=torch.bool)
+    padded[:, :, :Nk] = blocked
+    bits = (padded.view(B, Nq, words, 32).long() << torch.arange(32)).sum(-1)
+    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+    rowany = (~blocked).any(-1).to(torch.int32).flatten()
+    got = ops.mha_core_tc(q.cuda(), k.cuda(), v.cuda(), bits.cuda(), rowany.cuda()).cpu()
+    assert rel_err(got, _mha_ref(q, k, v, blocked)) < 1e-5
+
+
 @pytest.mark.parametrize("hw", [24, 1050, 4200])
 def test_attn_mask_bits(hw):
     from pairnet_b200 import ops
