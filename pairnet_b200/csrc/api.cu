@@ -331,13 +331,28 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
           {b.XP[l], b.XPlo[l], D, Whi, Wlo, D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk, D, D},
           {b.X[l], b.Xlo[l], D, Whi + (size_t)D * D, Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, Vc, D, Mk, D,
            D}};
-      if (fa_tc) {  // emit K split hi/lo and V transposed per image (keys contiguous) + split, for fa_umma_kernel
+      if (fa_tc) {
+        // operands for fa_umma_kernel: K split hi/lo; V^T per image (keys contiguous) computed directly as
+        // Wv . X_b^T (weights as the A operand, per-row bias) so its stores stay row-contiguous.
         o[0].C_lo = b.Klo2[i & 1];
-        o[1].C_lo = b.Vlo2[i & 1];
-        o[1].t_rows = p.hw[l];
-        o[1].ldc = fa.ldv;
+        UmmaOperand batch[4];
+        int nb = 0;
+        batch[nb++] = o[0];
+        for (int bi = 0; bi < p.B; ++bi) {
+          UmmaOperand v{Whi + (size_t)D * D, Wlo + (size_t)D * D, D,
+                        b.X[l] + (size_t)bi * p.hw[l] * D, b.Xlo[l] + (size_t)bi * p.hw[l] * D, D,
+                        Lw.cross_attn.in_proj_b + 2 * D, Vc + (size_t)bi * D * fa.ldv, fa.ldv, D, p.hw[l], D};
+          v.C_lo = b.Vlo2[i & 1] + (size_t)bi * D * fa.ldv;
+          v.bias_per_row = 1;
+          batch[nb++] = v;
+          if (nb == 4 || bi + 1 == p.B) {
+            PN_TRY(launch_umma_gemm(batch, nb, 3, s2));
+            nb = 0;
+          }
+        }
+      } else {
+        PN_TRY(launch_umma_gemm(o, 2, 3, s2));
       }
-      PN_TRY(launch_umma_gemm(o, 2, 3, s2));
     } else {
       GemmBatch g{};
       g.p[0] = make_linear(b.XP[l], D, Lw.cross_attn.in_proj_w + (size_t)D * D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk,

@@ -97,6 +97,7 @@ struct UmmaOperand {
   float* C_lo;   // optional: emit the result pre-split (C = hi, C_lo = lo) for a chained 3xTF32 GEMM
   int relu;
   int t_rows;    // > 0: transposed store C[(m / t_rows) * N + n][m % t_rows] with row pitch ldc (V^T per image)
+  int bias_per_row;  // bias indexed by output row (weights as the A operand, e.g. V^T = Wv . X^T)
 };
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st);

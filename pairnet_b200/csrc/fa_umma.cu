@@ -27,6 +27,12 @@ constexpr int TM_S = 0, TM_PHI = 128, TM_PLO = 256, TM_O = 384, TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 2 * TILE16K + (size_t)KV_STAGES * STAGE_BYTES + 1024 + 256;
 constexpr float NEG_BIG = -1.0e30f;
 
+__device__ __forceinline__ float fast_exp2(float x) {  // ex2.approx: 2 ulp, flushes tiny results to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Params {
   CUtensorMap q_hi, q_lo, k_hi, k_lo, vt_hi, vt_lo;
   const uint32_t* mask_bits; int mask_words;
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
           if (!((w[c] >> j) & 1u)) cmax = fmaxf(cmax, __uint_as_float(v[j]));
       }
       const float m_new = fmaxf(m_run, cmax);
-      const float corr = exp2f(m_run - m_new);
+      const float corr = fast_exp2(m_run - m_new);
       // pass 2: p = 2^(s - m_new), split hi/lo, store to TMEM as the A operand of P V
       float lsum = 0.f;
 #pragma unroll
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
         tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float p = ((w[c] >> j) & 1u) ? 0.f : exp2f(__uint_as_float(v[j]) - m_new);
+          const float p = ((w[c] >> j) & 1u) ? 0.f : fast_exp2(__uint_as_float(v[j]) - m_new);
           lsum += p;
           const float hi = rna_tf32(p);
           ph[j] = __float_as_uint(hi);

@@ -17,7 +17,7 @@ namespace umma {
 constexpr int BM = 128, BK = 32;            // BK fp32 = 128 B = one SWIZZLE_128B row
 constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
 // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each takes half the columns)
-constexpr int BIAS_MAX = 2048;              // per-problem bias staged in smem (epilogue reads it with LDS, not LDG)
+constexpr int BIAS_MAX = 1024;              // per-problem bias staged in smem (epilogue reads it with LDS, not LDG)
 // BN = 128: 3 stages x 64 KiB, 2 x 128 TMEM columns.  BN = 256 (N % 256 == 0): A tiles are re-read half as often;
 // 2 stages x 96 KiB, 2 x 256 TMEM columns (the whole TMEM).
 template <int BN>
@@ -27,7 +27,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // a_hi, a_lo, b_hi, b_lo
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr size_t SMEM_BYTES =
-      (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BIAS_MAX * sizeof(float);
+      (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BIAS_MAX * sizeof(float);
 };
 
 struct Problem {
@@ -38,8 +38,9 @@ struct Problem {
   int M, N, K, ldc;
   int relu;
   int t_rows;   // > 0: transposed store  C[(m / t_rows) * N + n][m % t_rows]  (row pitch ldc), e.g. V^T per image
+  int bias_per_row;  // bias indexed by the output row m instead of the column n (weights as the A operand)
 };
-constexpr int MAX_PROBLEMS = 2;
+constexpr int MAX_PROBLEMS = 4;
 struct Params {
   Problem p[MAX_PROBLEMS];
   int passes;  // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
@@ -82,13 +83,15 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
+  static_assert(MAX_PROBLEMS * BIAS_MAX * 4 <= 4 * 2048 * 4, "bias staging area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= 2) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
     for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += NUM_THREADS - 64) {  // epilogue threads
       const int pi = i / BIAS_MAX, n = i % BIAS_MAX;
       float bv = 0.f;
-      if (pi < prm.count && prm.p[pi].bias && n < prm.p[pi].N) bv = __ldg(prm.p[pi].bias + n);
+      if (pi < prm.count && prm.p[pi].bias && n < (prm.p[pi].bias_per_row ? prm.p[pi].M : prm.p[pi].N))
+        bv = __ldg(prm.p[pi].bias + n);
       bias_s[i] = bv;
     }
   }
@@ -196,6 +199,8 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
       const int row = tc.m0 + quad * 32 + lane;
       const int n0 = tc.n0;
       const float* bias_t = bias_s + tc.p * BIAS_MAX + n0;  // n0 + 127 < BIAS_MAX (checked on the host)
+      const float bias_row = P.bias_per_row ? bias_s[tc.p * BIAS_MAX + min(row, BIAS_MAX - 1)] : 0.f;
+      if (P.bias_per_row) bias_t = bias_s + tc.p * BIAS_MAX;  // (unused columns; keep the address in range)
 #pragma unroll 1
       for (int c0 = chalf * CH; c0 < (chalf + 1) * CH; c0 += 32) {
         uint32_t v[32];
@@ -233,7 +238,8 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
           for (int j = 0; j < 32; j += 4) {
             const int n = n0 + c0 + j;
             float o[4];
-            const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + j);
+            float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + j);
+            if (P.bias_per_row) bb = make_float4(bias_row, bias_row, bias_row, bias_row);
             const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -383,7 +389,8 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     const UmmaOperand& o = ops[i];
     PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || (o.a_lo && o.w_lo)), PN_ERR_BAD_ARG, "umma: null operand");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
-    PN_REQUIRE(cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N, BIAS_MAX);
+    PN_REQUIRE(o.bias_per_row || cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N,
+               BIAS_MAX);
     PN_REQUIRE(o.t_rows > 0 || (o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0), PN_ERR_UNSUPPORTED,
                "umma: C must be 16B aligned");
     Problem& p = prm.p[i];
@@ -392,7 +399,8 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     PN_TRY(make_map(&p.a_lo, passes == 3 ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
-    p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows;
+    p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
+    PN_REQUIRE(!o.bias_per_row || o.M <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: per-row bias needs M <= %d", BIAS_MAX);
     PN_REQUIRE(!o.C_lo || ((uintptr_t)o.C_lo & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C_lo must be 16B aligned");
     maxM = o.M > maxM ? o.M : maxM;
     maxN = o.N > maxN ? o.N : maxN;

@@ -264,7 +264,16 @@ class MSDeformAttnPixelDecoder(nn.Module):
             shapes.append(tuple(f.shape[-2:]))
             xs.append(self.input_convs[i](f).flatten(2).transpose(1, 2))
         pos_l, ref, norm = self._geometry(shapes, feats[0].device, feats[0].dtype)
-        pos = torch.cat([p + self.level_encoding.weight[i][None, :] for i, p in pos_l], 0)[None]
+        # sine position + level encoding: input independent -> cached until level_encoding changes
+        le = self.level_encoding.weight
+        key = (tuple(shapes), le.data_ptr(), le._version, torch.is_grad_enabled())
+        cached = self.__dict__.get("_pos_cache")
+        if cached is not None and cached[0] == key:
+            pos = cached[1]
+        else:
+            pos = torch.cat([p + le[i][None, :] for i, p in pos_l], 0)[None]
+            if not torch.is_grad_enabled():
+                self.__dict__["_pos_cache"] = (key, pos)
         x = torch.cat(xs, 1)
         if x.is_cuda and self.encoder_impl == "native" and not torch.is_grad_enabled():
             x = self._native_encoder(x.contiguous(), pos[0].contiguous(), shapes)
