@@ -82,6 +82,8 @@ PN_API int pn_get_option(int key);
 #define PN_OPT_OVERLAP 3        /* default 1: memory-side K/V projections and the output head run on an internal side
                                  * stream (fork/join with events; parallel branches under graph capture); 0 = one stream */
 #define PN_OPT_FA_TC 4          /* default 1: masked cross-attention of levels with >= 1024 tokens on tcgen05 (0 = FFMA) */
+#define PN_OPT_UMMA_RAW_A 5     /* default 1: activations enter the tcgen05 GEMM raw and are split hi/lo inside the SM
+                                 * (through TMEM) instead of being materialised pre-split by their producers */
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

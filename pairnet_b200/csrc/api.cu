@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 0, 0, 0};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 0};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -295,8 +295,13 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
       pos = b.pos[l];
     }
     const bool tc = get_option(OPT_TENSOR_CORES) && p.B * p.hw[l] >= TC_MIN_ROWS;
+    const bool raw_a = tc && get_option(OPT_UMMA_RAW_A);
+    // split forms needed by the tensor-core consumers: X as the B operand of V^T = Wv . X^T (always pre-split);
+    // X / XP as A operands only when the GEMM does not split A in-kernel
+    const bool x_split = tc && (get_option(OPT_FA_TC) || !raw_a);
+    const bool xp_split = tc && !raw_a;
     PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st,
-                             tc ? b.Xlo[l] : nullptr, tc ? b.XPlo[l] : nullptr));
+                             x_split ? b.Xlo[l] : nullptr, xp_split ? b.XPlo[l] : nullptr));
     PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
                                       st));
   }
@@ -321,6 +326,7 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     const int Mk = p.B * p.hw[l];
     const bool tc = get_option(OPT_TENSOR_CORES) && Mk >= TC_MIN_ROWS;
     const bool fa_tc = tc && get_option(OPT_FA_TC);
+    const bool raw_a = tc && get_option(OPT_UMMA_RAW_A);
     FaKV fa{Kc, b.Klo2[i & 1], Vc, b.Vlo2[i & 1], (int)round_up(p.hw[l], 4)};
     if (tc) {
       // tcgen05 path: TMA-staged tiles, UMMA kind::tf32 with hi/lo split operands (fp32 parity)
@@ -331,13 +337,21 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
           {b.XP[l], b.XPlo[l], D, Whi, Wlo, D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk, D, D},
           {b.X[l], b.Xlo[l], D, Whi + (size_t)D * D, Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, Vc, D, Mk, D,
            D}};
+      if (raw_a) {  // A operands enter raw; the kernel splits them through TMEM
+        o[0].a_lo = nullptr; o[0].a_is_raw = 1;
+        if (!fa_tc) { o[1].a_lo = nullptr; o[1].a_is_raw = 1; }
+      }
       if (fa_tc) {
         // operands for fa_umma_kernel: K split hi/lo; V^T per image (keys contiguous) computed directly as
         // Wv . X_b^T (weights as the A operand, per-row bias) so its stores stay row-contiguous.
         o[0].C_lo = b.Klo2[i & 1];
         UmmaOperand batch[4];
         int nb = 0;
-        batch[nb++] = o[0];
+        if (raw_a) {
+          PN_TRY(launch_umma_gemm(&o[0], 1, 3, s2));  // raw-A and split-A problems use different kernel variants
+        } else {
+          batch[nb++] = o[0];
+        }
         for (int bi = 0; bi < p.B; ++bi) {
           UmmaOperand v{Whi + (size_t)D * D, Wlo + (size_t)D * D, D,
                         b.X[l] + (size_t)bi * p.hw[l] * D, b.Xlo[l] + (size_t)bi * p.hw[l] * D, D,
@@ -597,8 +611,13 @@ int pn_linear_tc(const float* x, int ldx, const float* w, const float* b, float*
   float* wh = W.take<float>((size_t)N * K); float* wl = W.take<float>((size_t)N * K);
   PN_REQUIRE(W.ok() && xh && xl && wh && wl, PN_ERR_WORKSPACE, "linear_tc: workspace too small");
   cudaStream_t st = as_stream(stream);
-  PN_TRY(launch_split_tf32(x, xh, xl, (size_t)M * K, st));
   PN_TRY(launch_split_tf32(w, wh, wl, (size_t)N * K, st));
+  if (passes == 3 && get_option(OPT_UMMA_RAW_A)) {  // A split in-kernel (TMEM), no pre-pass over x
+    UmmaOperand o{x, nullptr, K, wh, wl, K, b, y, ldy, M, N, K};
+    o.a_is_raw = 1;
+    return launch_umma_gemm(&o, 1, passes, st);
+  }
+  PN_TRY(launch_split_tf32(x, xh, xl, (size_t)M * K, st));
   UmmaOperand o{xh, xl, K, wh, wl, K, b, y, ldy, M, N, K};
   return launch_umma_gemm(&o, 1, passes, st);
 }

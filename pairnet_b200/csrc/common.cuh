@@ -98,6 +98,7 @@ struct UmmaOperand {
   int relu;
   int t_rows;    // > 0: transposed store C[(m / t_rows) * N + n][m % t_rows] with row pitch ldc (V^T per image)
   int bias_per_row;  // bias indexed by output row (weights as the A operand, e.g. V^T = Wv . X^T)
+  int a_is_raw;      // a_hi points to the RAW fp32 A (a_lo unused): the kernel splits it in the SM through TMEM
 };
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st);
@@ -160,7 +161,7 @@ int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
                       int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_COUNT = 8 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_COUNT = 8 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);

@@ -237,8 +237,16 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
     PN_REQUIRE(e == cudaSuccess, (int)e, "msda_encoder: memcpy: %s", cudaGetErrorString(e));
     return 0;
   };
-  split_add_kernel<<<cdiv((long long)M * (D / 4), 256), 256, 0, st>>>(x_in, pos, nq, b.x_hi, b.x_lo, b.q_hi, b.q_lo, M);
-  PN_TRY(check_launch("split_add_kernel"));
+  // raw mode: activations enter the tcgen05 GEMM as plain fp32 and are split inside the SM (TMEM), so no
+  // producer materialises hi/lo copies; otherwise every producer emits its output pre-split.
+  const bool raw = get_option(OPT_UMMA_RAW_A) != 0;
+  float* q_raw = b.q_hi;  // raw mode: q = x + pos lives here
+  if (raw) {
+    PN_TRY(launch_add_rows(x_in, pos, q_raw, B, nq, st));
+  } else {
+    split_add_kernel<<<cdiv((long long)M * (D / 4), 256), 256, 0, st>>>(x_in, pos, nq, b.x_hi, b.x_lo, b.q_hi, b.q_lo, M);
+    PN_TRY(check_launch("split_add_kernel"));
+  }
   const float* x_cur = x_in;
   for (int i = 0; i < w->num_layers; ++i) {
     const PnMsdaEncoderLayer& Lw = w->layers[i];
@@ -260,32 +268,45 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
     {  // value = x Wv^T + bv ; ol = q [Wo;Wa]^T + [bo;ba]
       UmmaOperand o[2] = {{b.x_hi, b.x_lo, D, wv_hi, wv_lo, D, Lw.value_proj.b, b.value, D, Mi, D, D},
                           {b.q_hi, b.q_lo, D, wo_hi, wo_lo, D, b.b_ol, b.ol, ldo, Mi, n_ol, D}};
+      if (raw) {
+        o[0].a_hi = x_cur; o[0].a_lo = nullptr; o[0].a_is_raw = 1;
+        o[1].a_hi = q_raw; o[1].a_lo = nullptr; o[1].a_is_raw = 1;
+      }
       PN_TRY(launch_umma_gemm(o, 2, 3, st));
     }
     {
       dim3 grid(cdiv(nq, MSDA_TOK), NH, B);
-      msda_sample_kernel<<<grid, 256, 0, st>>>(b.value, b.ol, ldo, b.att_hi, b.att_lo, g, B);
+      msda_sample_kernel<<<grid, 256, 0, st>>>(b.value, b.ol, ldo, b.att_hi, raw ? nullptr : b.att_lo, g, B);
       PN_TRY(check_launch("msda_sample_kernel"));
     }
     {
-      UmmaOperand o{b.att_hi, b.att_lo, D, wp_hi, wp_lo, D, Lw.output_proj.b, b.proj, D, Mi, D, D};
+      UmmaOperand o{b.att_hi, raw ? nullptr : b.att_lo, D, wp_hi, wp_lo, D, Lw.output_proj.b, b.proj, D, Mi, D, D};
+      o.a_is_raw = raw;
       PN_TRY(launch_umma_gemm(&o, 1, 3, st));
       LnArgs n{};
       n.x = b.proj; n.nparts = 1; n.resid = x_cur; n.gamma = Lw.norm[0].gamma; n.beta = Lw.norm[0].beta;
-      n.y = b.x1; n.y_hi = b.x1_hi; n.y_lo = b.x1_lo; n.M = Mi;
+      n.y = b.x1; n.M = Mi;
+      if (!raw) { n.y_hi = b.x1_hi; n.y_lo = b.x1_lo; }
       PN_TRY(launch_layernorm(n, st));
     }
     {
       UmmaOperand o1{b.x1_hi, b.x1_lo, D, w1_hi, w1_lo, D, Lw.ffn1.b, b.h_hi, ffn, Mi, ffn, D, b.h_lo, 1};
+      if (raw) { o1.a_hi = b.x1; o1.a_lo = nullptr; o1.a_is_raw = 1; o1.C_lo = nullptr; }  // h stays raw fp32
       PN_TRY(launch_umma_gemm(&o1, 1, 3, st));
-      UmmaOperand o2{b.h_hi, b.h_lo, ffn, w2_hi, w2_lo, ffn, Lw.ffn2.b, b.y, D, Mi, D, ffn};
+      UmmaOperand o2{b.h_hi, raw ? nullptr : b.h_lo, ffn, w2_hi, w2_lo, ffn, Lw.ffn2.b, b.y, D, Mi, D, ffn};
+      o2.a_is_raw = raw;
       PN_TRY(launch_umma_gemm(&o2, 1, 3, st));
       const bool last = (i + 1 == w->num_layers);
       LnArgs n{};
       n.x = b.y; n.nparts = 1; n.resid = b.x1; n.gamma = Lw.norm[1].gamma; n.beta = Lw.norm[1].beta;
       n.y = last ? x_out : b.x; n.M = Mi;
       if (!last) {
-        n.y_hi = b.x_hi; n.y_lo = b.x_lo; n.pos = pos; n.pos_mod = nq; n.ypos_hi = b.q_hi; n.ypos_lo = b.q_lo;
+        n.pos = pos; n.pos_mod = nq;
+        if (raw) {
+          n.ypos = q_raw;
+        } else {
+          n.y_hi = b.x_hi; n.y_lo = b.x_lo; n.ypos_hi = b.q_hi; n.ypos_lo = b.q_lo;
+        }
       }
       PN_TRY(launch_layernorm(n, st));
       x_cur = b.x;

@@ -204,8 +204,8 @@ int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st) {
 }
 
 // mem [B,256,hw] -> x [B,hw,256] (+ level_embed) ; xp = x + pos.   32x32 smem transpose tiles.
-// x_lo/xp_lo != null: 3xTF32 operand form for the tcgen05 K/V projection -- x/xp receive hi = rna_tf32(v),
-// x_lo/xp_lo receive rna_tf32(v - hi).
+// x_lo (xp_lo) != null: 3xTF32 pre-split form -- x (xp) receives hi = rna_tf32(v), x_lo (xp_lo) receives
+// rna_tf32(v - hi); otherwise the raw fp32 value is stored.
 __global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict__ mem,
                                                           const float* __restrict__ level_embed,
                                                           const float* __restrict__ pos, float* __restrict__ x,
@@ -230,13 +230,17 @@ __global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict
       const size_t o = ((size_t)b * hw + p) * D + c;
       const float vp = v + __ldg(pos + (size_t)p * D + c);
       if (x_lo) {
-        const float h = rna_tf32f(v), hp = rna_tf32f(vp);
+        const float h = rna_tf32f(v);
         x[o] = h;
         x_lo[o] = rna_tf32f(v - h);
+      } else {
+        x[o] = v;
+      }
+      if (xp_lo) {
+        const float hp = rna_tf32f(vp);
         xp[o] = hp;
         xp_lo[o] = rna_tf32f(vp - hp);
       } else {
-        x[o] = v;
         xp[o] = vp;
       }
     }
@@ -246,7 +250,6 @@ int launch_level_prep(const float* mem, const float* level_embed, const float* p
                       int hw, cudaStream_t st, float* x_lo, float* xp_lo) {
   PN_REQUIRE(mem && level_embed && pos && x && xp && B > 0 && hw > 0, PN_ERR_BAD_ARG, "level_prep: bad args");
   dim3 grid(cdiv(hw, 32), D / 32, B);
-  PN_REQUIRE((x_lo == nullptr) == (xp_lo == nullptr), PN_ERR_BAD_ARG, "level_prep: lo outputs come in pairs");
   level_prep_kernel<<<grid, 256, 0, st>>>(mem, level_embed, pos, x, xp, x_lo, xp_lo, hw);
   return check_launch("level_prep_kernel");
 }

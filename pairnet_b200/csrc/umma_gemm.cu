@@ -30,6 +30,9 @@ struct Cfg {
       (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BIAS_MAX * sizeof(float);
 };
 
+// raw-A variant: 4 stages x (A raw 16 KiB + B hi/lo 32 KiB)
+constexpr size_t RAW_SMEM_BYTES = (size_t)4 * (A_TILE_BYTES + 2 * 128 * BK * 4) + 1024 + 256 + 4 * BIAS_MAX * sizeof(float);
+
 struct Problem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;  // A [M,K], W [N,K]; box 32 x 128, SWIZZLE_128B
   const float* bias;
@@ -67,27 +70,43 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
   return c;
 }
 
-// Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM owner), warps2-5 = epilogue.
-// Two 128-column TMEM accumulators ping-pong so the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int NUM_EPI_WARPS>
-__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(const __grid_constant__ Params prm) {
-  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp0 TMA, warp1 MMA + TMEM alloc, then epilogue warps
-  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
-  constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES, OFF_B_HI = 2 * A_TILE_BYTES,
-                OFF_B_LO = 2 * A_TILE_BYTES + Cfg<BN>::B_TILE_BYTES;
+// Persistent, warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM owner), warps2-5 = epilogue,
+// (A_RAW only) warps6-9 = A splitter.  Two 128-column TMEM accumulators ping-pong so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+//
+// A_RAW = true: the A operand is loaded RAW (plain fp32, one 16 KiB tile per k-block instead of a hi and a lo
+// tile) and split in the SM: four splitter warps read the swizzled tile (one row per thread), compute
+// hi = rna_tf32(a), lo = rna_tf32(a - hi) and park both in tensor memory with tcgen05.st; the MMAs then take A
+// from TMEM (tcgen05.mma with a TMEM A operand) and only B (weights, pre-split) from shared memory.  This halves
+// the A bytes moved through HBM/L2 and frees smem for a 4th pipeline stage.
+template <int BN, int NUM_EPI_WARPS, bool A_RAW>
+__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? 128 : 0), 1)
+umma_gemm_kernel(const __grid_constant__ Params prm) {
+  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + (A_RAW ? 128 : 0);
+  constexpr int STAGES = A_RAW ? 4 : Cfg<BN>::STAGES;
+  constexpr int B_TILE = Cfg<BN>::B_TILE_BYTES;
+  constexpr int STAGE_BYTES = A_RAW ? (A_TILE_BYTES + 2 * B_TILE) : Cfg<BN>::STAGE_BYTES;
+  constexpr int TMEM_COLS = A_RAW ? 512 : Cfg<BN>::TMEM_COLS;
+  constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES;
+  constexpr int OFF_B_HI = A_RAW ? A_TILE_BYTES : 2 * A_TILE_BYTES;
+  constexpr int OFF_B_LO = OFF_B_HI + B_TILE;
+  constexpr int TM_A = 2 * BN;  // A_RAW: TMEM columns [TM_A + set*64, +32) = hi, [+32, +64) = lo
+  static_assert(!A_RAW || BN == 128, "raw-A variant is built for 128x128 tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* a_ready_bar = tmem_empty_bar + 2;     // [2]  splitter -> MMA   (A_RAW)
+  uint64_t* a_free_bar = a_ready_bar + 2;         // [2]  MMA -> splitter   (A_RAW)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_free_bar + 2);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
-  static_assert(MAX_PROBLEMS * BIAS_MAX * 4 <= 4 * 2048 * 4, "bias staging area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= 2) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
-    for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += NUM_THREADS - 64) {  // epilogue threads
+  const bool is_epi = warp >= 2 && warp < 2 + NUM_EPI_WARPS;
+  if (is_epi) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
+    for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += 32 * NUM_EPI_WARPS) {
       const int pi = i / BIAS_MAX, n = i % BIAS_MAX;
       float bv = 0.f;
       if (pi < prm.count && prm.p[pi].bias && n < (prm.p[pi].bias_per_row ? prm.p[pi].M : prm.p[pi].N))
@@ -99,15 +118,17 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], A_RAW ? 5 : 1);  // MMA commit (+ the 4 splitter warps that read the raw A tile)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&a_ready_bar[a], 4);
+      mbar_init(&a_free_bar[a], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // whole warp allocates both accumulators
+  if (warp == 1) {  // whole warp allocates the accumulators (+ the A staging columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
                  "r"(TMEM_COLS)
                  : "memory");
@@ -131,15 +152,16 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-          const uint32_t bytes = (prm.passes == 3) ? STAGE_BYTES : STAGE_BYTES / 2;
+          const uint32_t bytes = A_RAW ? (uint32_t)STAGE_BYTES
+                                       : ((prm.passes == 3) ? (uint32_t)STAGE_BYTES : (uint32_t)STAGE_BYTES / 2);
           mbar_expect_tx(&full_bar[s], bytes);
           // B tiles are loaded as BN/128 boxes of 128 rows (the tensor-map box is 32 x 128)
-          tma_load_2d(st + OFF_A_HI, &P.a_hi, &full_bar[s], kb * BK, tc.m0);
+          tma_load_2d(st + OFF_A_HI, &P.a_hi, &full_bar[s], kb * BK, tc.m0);  // A_RAW: a_hi holds the raw A map
 #pragma unroll
           for (int h = 0; h < BN / 128; ++h)
             tma_load_2d(st + OFF_B_HI + h * A_TILE_BYTES, &P.b_hi, &full_bar[s], kb * BK, tc.n0 + h * 128);
-          if (prm.passes == 3) {
-            tma_load_2d(st + OFF_A_LO, &P.a_lo, &full_bar[s], kb * BK, tc.m0);
+          if (A_RAW || prm.passes == 3) {
+            if (!A_RAW) tma_load_2d(st + OFF_A_LO, &P.a_lo, &full_bar[s], kb * BK, tc.m0);
 #pragma unroll
             for (int h = 0; h < BN / 128; ++h)
               tma_load_2d(st + OFF_B_LO + h * A_TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, tc.n0 + h * 128);
@@ -163,29 +185,46 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(st + OFF_A_HI), a_lo = make_smem_desc(st + OFF_A_LO);
           const uint64_t b_hi = make_smem_desc(st + OFF_B_HI), b_lo = make_smem_desc(st + OFF_B_LO);
+          if (A_RAW) {
+            const uint32_t set = it & 1;
+            mbar_wait(&a_ready_bar[set], (it >> 1) & 1);  // splitter has parked hi/lo of this k-block in TMEM
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi_t = tmem_base + TM_A + set * 64, a_lo_t = a_hi_t + 32;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
-            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-            if (prm.passes == 3) {
-              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
-              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+              const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+              umma_tf32_ts(d_tmem, a_lo_t + k * UMMA_K, b_hi + koff, idesc, first);
+              umma_tf32_ts(d_tmem, a_hi_t + k * UMMA_K, b_lo + koff, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi_t + k * UMMA_K, b_hi + koff, idesc, 1u);
             }
+            umma_commit(&empty_bar[s]);      // B tiles of this stage are free once these MMAs complete
+            umma_commit(&a_free_bar[set]);   // ... and so is the TMEM A set
+          } else {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t a_hi = make_smem_desc(st + OFF_A_HI), a_lo = make_smem_desc(st + OFF_A_LO);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
+              const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+              if (prm.passes == 3) {
+                umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
+                umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
+              }
+            }
+            umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
     }
-  } else {
-    // ===== epilogue: warps 2..9 -> TMEM lane quadrant (warp % 4), column half ((warp - 2) / 4)
+  } else if (is_epi) {
+    // ===== epilogue: TMEM lane quadrant (warp % 4), column slice ((warp - 2) / 4)
     const int quad = warp & 3;
     const int chalf = (warp - 2) >> 2;
     constexpr int CH = BN / (NUM_EPI_WARPS / 4);  // columns per epilogue warp
@@ -271,6 +310,45 @@ __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS, 1) umma_gemm_kernel(c
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (A_RAW) {
+    // ===== A splitter: raw fp32 tile (smem, SWIZZLE_128B) -> hi / lo in tensor memory, one row per thread
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord<BN>(prm, t);
+      const int num_kb = prm.p[tc.p].K / BK;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t set = it & 1;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);          // raw tile has landed
+        mbar_wait(&a_free_bar[set], ((it >> 1) & 1) ^ 1);    // MMAs of k-block it-2 have finished with this set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint8_t* arow = smem + (size_t)s * STAGE_BYTES + OFF_A_HI + r * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // logical 16-byte chunk c of the row lives at physical chunk c ^ (r & 7)
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+          const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float h = rna_tf32(x[u]);
+            hi[c * 4 + u] = __float_as_uint(h);
+            lo[c * 4 + u] = __float_as_uint(rna_tf32(x[u] - h));
+          }
+        }
+        tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64, hi);
+        tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64 + 32, lo);
+        tmem_st_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_ready_bar[set]);
+          mbar_arrive(&empty_bar[s]);  // this warp is done with the raw tile in smem
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -387,7 +465,9 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   int maxM = 0, maxN = 0;
   for (int i = 0; i < count; ++i) {
     const UmmaOperand& o = ops[i];
-    PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || (o.a_lo && o.w_lo)), PN_ERR_BAD_ARG, "umma: null operand");
+    PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || ((o.a_lo || o.a_is_raw) && o.w_lo)), PN_ERR_BAD_ARG,
+               "umma: null operand");
+    PN_REQUIRE(!o.a_is_raw || passes == 3, PN_ERR_BAD_ARG, "umma: raw A operands need passes == 3");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
     PN_REQUIRE(o.bias_per_row || cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N,
                BIAS_MAX);
@@ -396,7 +476,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     Problem& p = prm.p[i];
     PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
-    PN_TRY(make_map(&p.a_lo, passes == 3 ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
+    PN_TRY(make_map(&p.a_lo, (passes == 3 && !o.a_is_raw) ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
     p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
@@ -407,18 +487,23 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg<128>::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)Cfg<128>::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(umma_gemm_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(umma_gemm_kernel<256, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)Cfg<256>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RAW_SMEM_BYTES);
     PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  bool wide = get_option(OPT_UMMA_WIDE) != 0;
+  bool raw = passes == 3;
+  for (int i = 0; i < count; ++i) raw = raw && ops[i].a_is_raw;
+  bool wide = !raw && get_option(OPT_UMMA_WIDE) != 0;
   for (int i = 0; i < count; ++i) wide = wide && (ops[i].N % 256 == 0);
   const int BN = wide ? 256 : 128;
   prm.count = count;
@@ -432,12 +517,14 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
-  if (wide)
-    umma_gemm_kernel<256, 8><<<grid, 64 + 32 * 8, Cfg<256>::SMEM_BYTES, st>>>(prm);
+  if (raw)
+    umma_gemm_kernel<128, 4, true><<<grid, 64 + 32 * 4 + 128, RAW_SMEM_BYTES, st>>>(prm);
+  else if (wide)
+    umma_gemm_kernel<256, 8, false><<<grid, 64 + 32 * 8, Cfg<256>::SMEM_BYTES, st>>>(prm);
   else if (get_option(OPT_UMMA_EPI8))
-    umma_gemm_kernel<128, 8><<<grid, 64 + 32 * 8, Cfg<128>::SMEM_BYTES, st>>>(prm);
+    umma_gemm_kernel<128, 8, false><<<grid, 64 + 32 * 8, Cfg<128>::SMEM_BYTES, st>>>(prm);
   else
-    umma_gemm_kernel<128, 4><<<grid, 64 + 32 * 4, Cfg<128>::SMEM_BYTES, st>>>(prm);
+    umma_gemm_kernel<128, 4, false><<<grid, 64 + 32 * 4, Cfg<128>::SMEM_BYTES, st>>>(prm);
   return check_launch("umma_gemm_kernel");
 }
 
