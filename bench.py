@@ -236,9 +236,9 @@ def dominant_kernel_roofline(model, device, pk):
     nat.check(lib.pn_split_tf32(w.data_ptr(), wh.data_ptr(), wl.data_ptr(), w.numel(), st), "pn_split_tf32")
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
 
-    def launch():
-        nat.check(lib.pn_linear_tc_presplit(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(),
-                                            y.data_ptr(), 2 * d, M, 2 * d, d, 3, st), "pn_linear_tc_presplit")
+    def launch():  # production variant: A enters raw and is split hi/lo inside the SM through TMEM
+        nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(), y.data_ptr(), 2 * d,
+                                        M, 2 * d, d, st), "pn_linear_tc_rawa")
     for _ in range(3):
         launch()
     ts = time_steps(launch, 10, flush, torch.cuda.current_stream())
@@ -251,12 +251,13 @@ def dominant_kernel_roofline(model, device, pk):
                                 st), "pn_linear")
     launch_ffma()
     ms_ffma = statistics.mean(time_steps(launch_ffma, 5, flush, torch.cuda.current_stream()))
-    alg_bytes = 4.0 * (2 * M * d + 2 * 2 * d * d + M * 2 * d)  # A hi+lo, W hi+lo, C
-    return {"bound": "tensor", "kernel": "umma_gemm_kernel: tcgen05.mma kind::tf32 x3 (fp32-parity split), K/V projection "
-                                         "of the 100x167 level, M=33400 N=512 K=256",
+    alg_bytes = 4.0 * (M * d + 2 * 2 * d * d + M * 2 * d)  # A (raw fp32), W hi+lo, C
+    return {"bound": "tensor", "kernel": "umma_gemm_kernel<128,4,raw-A>: tcgen05.mma kind::tf32 x3 (fp32-parity hi/lo split, A "
+                                         "split in-SM through TMEM), K/V-projection problem of the 100x167 level, "
+                                         "M=33400 N=512 K=256",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": 87.48e6, "traffic_source": "ncu --set full r01 capture (profiles/r01_umma_gemm_ncu.md): "
-                                                  "dram read 69.59 MB + write 17.90 MB per launch",
+            "traffic": 54.48e6, "traffic_source": "ncu --set full r01 capture (profiles/r01_umma_gemm_ncu.md): "
+                                                  "dram read 35.32 MB + write 19.16 MB per launch",
             "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": flops, "tensor_pipe_flops_per_launch": 3 * flops,
             "peak_source": pk["source"], "ffma_kernel_ms_same_problem": ms_ffma,

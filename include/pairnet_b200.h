@@ -124,6 +124,9 @@ PN_API int pn_linear_tc(const float* x, int ldx, const float* w, const float* b,
 /* the two halves of pn_linear_tc, for callers that keep operands pre-split (and for timing the GEMM alone):
  * hi = rna_tf32(x), lo = rna_tf32(x - hi) over n floats (n % 4 == 0); then the tcgen05 GEMM on split operands. */
 PN_API int pn_split_tf32(const float* x, float* hi, float* lo, size_t n, pn_stream_t stream);
+/* raw-A variant (default in production): x stays plain fp32 and is split inside the SM through TMEM */
+PN_API int pn_linear_tc_rawa(const float* x, const float* w_hi, const float* w_lo, const float* b, float* y,
+                             int ldy, int M, int N, int K, pn_stream_t stream);
 PN_API int pn_linear_tc_presplit(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                                  const float* b, float* y, int ldy, int M, int N, int K, int passes,
                                  pn_stream_t stream);

@@ -626,6 +626,13 @@ int pn_split_tf32(const float* x, float* hi, float* lo, size_t n, pn_stream_t st
   return launch_split_tf32(x, hi, lo, n, as_stream(stream));
 }
 
+int pn_linear_tc_rawa(const float* x, const float* w_hi, const float* w_lo, const float* b, float* y, int ldy, int M,
+                      int N, int K, pn_stream_t stream) {
+  UmmaOperand o{x, nullptr, K, w_hi, w_lo, K, b, y, ldy, M, N, K};
+  o.a_is_raw = 1;
+  return launch_umma_gemm(&o, 1, 3, as_stream(stream));
+}
+
 int pn_linear_tc_presplit(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* b,
                           float* y, int ldy, int M, int N, int K, int passes, pn_stream_t stream) {
   UmmaOperand o{x_hi, x_lo, K, w_hi, w_lo, K, b, y, ldy, M, N, K};

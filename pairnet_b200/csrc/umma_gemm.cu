@@ -90,7 +90,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES;
   constexpr int OFF_B_HI = A_RAW ? A_TILE_BYTES : 2 * A_TILE_BYTES;
   constexpr int OFF_B_LO = OFF_B_HI + B_TILE;
-  constexpr int TM_A = 2 * BN;  // A_RAW: TMEM columns [TM_A + set*64, +32) = hi, [+32, +64) = lo
+  constexpr int TM_A = 2 * BN;  // A_RAW: TMEM columns [TM_A + set*64, +32) = hi, [+32, +64) = lo  (4 sets -> 512 total)
   static_assert(!A_RAW || BN == 128, "raw-A variant is built for 128x128 tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,9 +98,10 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* a_ready_bar = tmem_empty_bar + 2;     // [2]  splitter -> MMA   (A_RAW)
-  uint64_t* a_free_bar = a_ready_bar + 2;         // [2]  MMA -> splitter   (A_RAW)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_free_bar + 2);
+  constexpr int ASETS = 4;                        // TMEM A staging sets (hi 32 + lo 32 columns each)
+  uint64_t* a_ready_bar = tmem_empty_bar + 2;     // [ASETS]  splitter -> MMA   (A_RAW)
+  uint64_t* a_free_bar = a_ready_bar + ASETS;     // [ASETS]  MMA -> splitter   (A_RAW)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_free_bar + ASETS);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,6 +124,8 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);  // one arrive per epilogue warp
+    }
+    for (int a = 0; a < ASETS; ++a) {
       mbar_init(&a_ready_bar[a], 4);
       mbar_init(&a_free_bar[a], 1);
     }
@@ -188,8 +191,8 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
           const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint64_t b_hi = make_smem_desc(st + OFF_B_HI), b_lo = make_smem_desc(st + OFF_B_LO);
           if (A_RAW) {
-            const uint32_t set = it & 1;
-            mbar_wait(&a_ready_bar[set], (it >> 1) & 1);  // splitter has parked hi/lo of this k-block in TMEM
+            const uint32_t set = it % ASETS;
+            mbar_wait(&a_ready_bar[set], (it / ASETS) & 1);  // splitter has parked hi/lo of this k-block in TMEM
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi_t = tmem_base + TM_A + set * 64, a_lo_t = a_hi_t + 32;
 #pragma unroll
@@ -321,9 +324,9 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
       const int num_kb = prm.p[tc.p].K / BK;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
-        const uint32_t set = it & 1;
-        mbar_wait(&full_bar[s], (it / STAGES) & 1);          // raw tile has landed
-        mbar_wait(&a_free_bar[set], ((it >> 1) & 1) ^ 1);    // MMAs of k-block it-2 have finished with this set
+        const uint32_t set = it % ASETS;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);               // raw tile has landed
+        mbar_wait(&a_free_bar[set], ((it / ASETS) & 1) ^ 1);      // MMAs of k-block it-ASETS are done with this set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* arow = smem + (size_t)s * STAGE_BYTES + OFF_A_HI + r * 128;
         uint32_t hi[32], lo[32];
@@ -498,6 +501,9 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)RAW_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RAW_SMEM_BYTES);
     PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -517,7 +523,9 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
-  if (raw)
+  if (raw && get_option(OPT_UMMA_EPI8))
+    umma_gemm_kernel<128, 8, true><<<grid, 64 + 32 * 8 + 128, RAW_SMEM_BYTES, st>>>(prm);
+  else if (raw)
     umma_gemm_kernel<128, 4, true><<<grid, 64 + 32 * 4 + 128, RAW_SMEM_BYTES, st>>>(prm);
   else if (wide)
     umma_gemm_kernel<256, 8, false><<<grid, 64 + 32 * 8, Cfg<256>::SMEM_BYTES, st>>>(prm);

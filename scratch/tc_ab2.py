@@ -16,5 +16,8 @@ def run(M,N,K, raw):
     ref = (x.double()@w.double().t()+b.double()).float()
     err = float((y-ref).abs().max()/ref.abs().max())
     print(f"raw={raw} M={M} N={N} K={K}: {tot/10*1e3:.1f} us incl. splits  {2*M*N*K/(tot/10)/1e9:.0f} TF/s alg  err {err:.2e}")
-for shp in ((33400,512,256),(43900,256,256),(43900,1024,256),(43900,256,1024),(43900,288,256),(1000,256,256)):
-    for raw in (0,1): run(*shp, raw)
+for epi8 in (0, 1):
+    lib.pn_set_option(2, epi8)
+    print("epi8", epi8)
+    for shp in ((33400,512,256),(43900,256,256),(43900,1024,256),(43900,256,1024),(43900,288,256)):
+        run(*shp, 1)
