@@ -15,13 +15,14 @@ bricks that forward instantiates (restated from the in-repo copies at
 published upstream algorithms).
 
 PARITY PINNING STATUS
-* ``ConvTiny`` (Matrix-Learner filter) is PINNED: the
-  reference's own ``pairnet/models/frameworks/cnn_factory.py`` imports here, and
-  ``oracle/make_golden.py`` ran it to mint ``tests/golden/convtiny_*.npz``.
-* Every other row is UNPINNED by the reference ("parity unpinned"): the
-  reference ships no tests / golden vectors and cannot be imported in this
-  container (mmcv, mmdet, detectron2, panopticapi absent, no network).  Those
-  rows are anchored on the same torch primitives the reference calls
-  (``nn.MultiheadAttention``, ``nn.LayerNorm``, ``F.interpolate``,
-  ``torch.topk``, ``torch.gather``) at the cited call sites.
+* ``CrossHead2.forward`` / ``forward_head`` (the op order, the top-k / gather / concat
+  index logic, the parameter names) is PINNED to the reference's own source: ``oracle/pin_reference.py``
+  executes ``/root/reference/pairnet/models/relation_heads/pairnet_head.py`` itself (plus the reference's
+  ``cnn_factory.py`` and the ``MultiheadAttention2`` / ``BaseTransformerLayer2`` forwards of
+  ``facebook_detr.py``) over constructor shims for the absent mmcv/mmdet, loads the oracle's weights with
+  ``strict=True`` and requires BIT-EQUAL outputs; its outputs are committed as ``tests/golden/head_ref_*.npz``.
+* ``ConvTiny`` (row 6) is PINNED on its own as well (``oracle/make_golden.py`` -> ``convtiny_ref_*.npz``).
+* Still "parity unpinned" (restated from the published upstream algorithm, not on disk): the constructors /
+  defaults of mmcv ``MultiheadAttention`` / ``BaseTransformerLayer``, mmcv ``FFN.forward``, mmdet
+  ``SinePositionalEncoding.forward``, and everything upstream of the hot path (pixel decoder, backbone).
 """

@@ -40,8 +40,10 @@ class OMultiheadAttention(nn.Module):
             query = query + query_pos
         if key_pos is not None:
             key = key + key_pos
+        # mmcv calls ``self.attn(...)[0]`` with torch's default need_weights=True: the explicit
+        # baddbmm -> softmax -> bmm path, not scaled_dot_product_attention.  Keep that arithmetic.
         out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
-                        need_weights=False)[0]
+                        need_weights=True)[0]
         return identity + out  # proj_drop / dropout_layer are identities (p = 0)
 
 

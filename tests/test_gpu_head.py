@@ -252,3 +252,44 @@ def test_overlap_and_tensor_core_options_are_result_neutral(heads):
     finally:
         lib.pn_set_option(3, 1)
         lib.pn_set_option(0, 1)
+
+
+def _ref_cases():
+    from oracle.pin_reference import REF_CASES
+    return REF_CASES
+
+
+@pytest.mark.parametrize("tag,B,hw4,seed,N,R", _ref_cases())
+def test_head_matches_reference_forward_golden(tag, B, hw4, seed, N, R):
+    """The B200 head against fixtures minted by the REFERENCE's own ``CrossHead2.forward`` (executed from
+    /root/reference by ``oracle/pin_reference.py``; nothing of the oracle is involved at run time except the
+    shared synthetic weights/inputs generator)."""
+    from oracle.head import HeadHyper, OCrossHead2
+    from oracle.make_golden import small_head_inputs
+    from oracle.weights import fixture_state_dict
+    from pairnet_b200.registry import build_head
+    from tests.util import product_head_cfg
+    g = np.load(os.path.join(GOLDEN, f"head_ref_{tag}.npz"))
+    shell = OCrossHead2(HeadHyper(num_obj_query=N, num_rel_query=R, with_pixel_decoder=False))
+    cfg = product_head_cfg()
+    cfg.update(pixel_decoder=None, num_obj_query=N, num_rel_query=R)
+    p = build_head(cfg)
+    p.load_state_dict(fixture_state_dict(shell, 10086), strict=True)
+    p = p.cuda().eval()
+    mf, mems = small_head_inputs(B, hw4, seed)
+    taps = {}
+    cls, msk = _run_product(p, mf, mems, taps)
+    assert rel_err(cls["cls"], g["cls"]) < RTOL_LOGITS
+    assert rel_err(cls["importance"], g["importance"]) < RTOL_LOGITS
+    assert rel_err(msk["mask"][:, :, ::4, ::4], g["mask_sub4"]) < RTOL_LOGITS
+    tol = RTOL_LOGITS * float(np.abs(g["importance"]).max())
+    swapped = check_topk_tie_aware(g["importance"], taps["sub_pos"], taps["obj_pos"], g["sub_pos"], g["obj_pos"], tol)
+    assert swapped <= 4
+    if swapped == 0:   # top-k indices bit-exact -> every downstream tensor is comparable
+        assert np.array_equal(taps["sub_pos"].cpu().numpy(), g["sub_pos"])
+        assert np.array_equal(taps["obj_pos"].cpu().numpy(), g["obj_pos"])
+        assert rel_err(cls["rel"], g["rel"]) < RTOL_LOGITS
+        assert rel_err(cls["sub"], g["sub"]) < RTOL_LOGITS
+        assert rel_err(cls["obj"], g["obj"]) < RTOL_LOGITS
+        assert rel_err(msk["sub_seg"][:, :, ::4, ::4], g["sub_seg_sub4"]) < RTOL_LOGITS
+        assert rel_err(msk["obj_seg"][:, :, ::4, ::4], g["obj_seg_sub4"]) < RTOL_LOGITS

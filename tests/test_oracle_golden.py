@@ -1,5 +1,7 @@
-"""CPU: the oracle against the committed golden vectors (ConvTiny fixtures were produced by the
-REFERENCE's own ``cnn_factory.ConvTiny``; head fixtures are the oracle's own regression anchors)."""
+"""CPU: the oracle against the committed golden vectors.  ``convtiny_ref_*`` were produced by the REFERENCE's
+own ``cnn_factory.ConvTiny``; ``head_ref_*`` by the REFERENCE's own ``CrossHead2.forward`` executed from
+``/root/reference`` over constructor shims for the absent mmcv/mmdet (``oracle/pin_reference.py``);
+``head_small_*`` are the oracle's own regression anchors."""
 import os
 
 import numpy as np
@@ -8,6 +10,7 @@ import torch
 
 from oracle.head import OConvTiny, stable_topk
 from oracle.make_golden import CONV_CASES, HEAD_CASES, build_small_head, small_head_inputs
+from oracle.pin_reference import REF_CASES
 from oracle.weights import numpy_state_dict, numpy_tensor
 from tests.util import GOLDEN, rel_err
 
@@ -56,6 +59,48 @@ def test_head_oracle_regression(tag, B, hw4, seed):
     # indices: equal except for near-ties
     same = (tr["sub_pos"].numpy() == g["sub_pos"]) & (tr["obj_pos"].numpy() == g["obj_pos"])
     assert same.mean() > 0.9
+
+
+def _ref_case_oracle(B, hw4, seed, N, R):
+    from oracle.head import HeadHyper, OCrossHead2
+    from oracle.weights import fixture_state_dict
+    o = OCrossHead2(HeadHyper(with_pixel_decoder=False, num_obj_query=N, num_rel_query=R)).eval()
+    o.load_state_dict(fixture_state_dict(o, 10086))
+    mf, mems = small_head_inputs(B, hw4, seed)
+    tr = {}
+    with torch.no_grad():
+        cls, msk = o.forward_from_memories(mf, mems, trace=tr)
+    return cls, msk, tr
+
+
+@pytest.mark.parametrize("tag,B,hw4,seed,N,R", REF_CASES)
+def test_head_oracle_matches_reference_forward_golden(tag, B, hw4, seed, N, R):
+    """Fixtures minted by the reference's own CrossHead2.forward (bit-equal to the oracle in the dev container;
+    here a small tolerance absorbs CPU-kernel differences between hosts)."""
+    g = np.load(os.path.join(GOLDEN, f"head_ref_{tag}.npz"))
+    cls, msk, tr = _ref_case_oracle(B, hw4, seed, N, R)
+    for k in ("cls", "rel", "importance", "sub", "obj"):
+        assert cls[k].shape == g[k].shape
+        assert rel_err(cls[k], g[k]) < 1e-4, k
+    assert rel_err(msk["mask"][:, :, ::4, ::4], g["mask_sub4"]) < 1e-4
+    assert rel_err(msk["sub_seg"][:, :, ::4, ::4], g["sub_seg_sub4"]) < 1e-4
+    assert rel_err(msk["obj_seg"][:, :, ::4, ::4], g["obj_seg_sub4"]) < 1e-4
+    same = (tr["sub_pos"].numpy() == g["sub_pos"]) & (tr["obj_pos"].numpy() == g["obj_pos"])
+    assert same.mean() > 0.9
+
+
+def test_oracle_bit_equals_live_reference_forward_if_present():
+    """Dev container only: execute the reference's CrossHead2.forward from /root/reference (subprocess: the
+    harness installs mmcv/mmdet constructor shims into sys.modules) and require bit-equality with the oracle."""
+    if not os.path.isdir("/root/reference/pairnet"):
+        pytest.skip("reference tree not present on this box")
+    import subprocess
+    import sys
+    from tests.util import ROOT
+    r = subprocess.run([sys.executable, "-m", "oracle.pin_reference", "--check"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("pinned ") == len(REF_CASES)
 
 
 def test_stable_topk_contract():
