@@ -82,10 +82,38 @@ class ResNet(nn.Module):
         self.__dict__["_fused_cache"] = (state, fused)
         return fused
 
+    fuse_epilogues = True  # bias / residual add / ReLU inside the cuDNN convolution epilogue (one kernel per conv)
+
+    @staticmethod
+    def _conv_act(x, conv, relu=True, residual=None):
+        """conv (+ folded-BN bias) (+ residual) (+ ReLU) as ONE cuDNN fused-epilogue call."""
+        if residual is not None:
+            return torch.cudnn_convolution_add_relu(x, conv.weight, residual, 1.0, conv.bias, conv.stride, conv.padding,
+                                                    conv.dilation, conv.groups)
+        if relu:
+            return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation,
+                                                conv.groups)
+        return conv(x)
+
+    def _forward_fused_epilogues(self, f, x):
+        x = self.maxpool(self._conv_act(x, f[0]))
+        outs = []
+        for i in range(4):
+            for blk in f[i + 1]:
+                identity = x if blk.downsample is None else blk.downsample[0](x)
+                y = self._conv_act(x, blk.conv1)
+                y = self._conv_act(y, blk.conv2)
+                x = self._conv_act(y, blk.conv3, residual=identity)
+            if i in self.out_indices:
+                outs.append(x)
+        return tuple(outs)
+
     def forward(self, x):
         if not self.training and not torch.is_grad_enabled() and x.is_cuda and self.norm_eval:
             f = self._fused()
             x = x.contiguous(memory_format=torch.channels_last)
+            if self.fuse_epilogues:
+                return self._forward_fused_epilogues(f, x)
             x = self.maxpool(torch.relu_(f[0](x)))
             outs = []
             for i in range(4):
