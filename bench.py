@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU oracle leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--ppn-microbench", action="store_true", help="also run BASELINE config 5 (PPN only)")
+    ap.add_argument("--no-ppn-microbench", action="store_true", help="skip BASELINE config 5 (PPN only, ~2 s)")
     ap.add_argument("--profile", action="store_true",
                     help="warm up, then run ONE eager forward between cudaProfilerStart/Stop and exit "
                          "(for `ncu --profile-from-start off`)")
@@ -380,7 +380,7 @@ def run_b200(args, rank, world, local):
         clk = clocks.stop()
 
         roof = dominant_kernel_roofline(model, device, pk) if rank == 0 else None
-        micro = ppn_microbench(device, pk) if (rank == 0 and args.ppn_microbench) else None
+        micro = ppn_microbench(device, pk) if (rank == 0 and not args.no_ppn_microbench) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

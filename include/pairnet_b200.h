@@ -84,6 +84,10 @@ PN_API int pn_get_option(int key);
 #define PN_OPT_FA_TC 4          /* default 1: masked cross-attention of levels with >= 1024 tokens on tcgen05 (0 = FFMA) */
 #define PN_OPT_UMMA_RAW_A 5     /* default 1: activations enter the tcgen05 GEMM raw and are split hi/lo inside the SM
                                  * (through TMEM) instead of being materialised pre-split by their producers */
+#define PN_OPT_TOPK_RADIX 6     /* default 0: top-k by local-maxima threshold + candidate ranking; 1 = always the exact
+                                 * 4-pass radix select (the fallback of the default path; parity studies) */
+#define PN_OPT_PPN_TC 7         /* default 1: pair matrix S.O^T of batches with >= 1024 embedding rows on tcgen05 (3xTF32,
+                                 * operands split in the SM); 0 = exact-fp32 FFMA */
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 0};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -223,6 +223,7 @@ static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
 }
 
 constexpr int TC_MIN_ROWS = 1024;  // memory levels with fewer tokens stay on the FFMA GEMM
+constexpr size_t PPN_L2_CHUNK_BYTES = 48u << 20;  // pair matrices of one PPN chunk (L2 is 126 MB)
 struct M2FBuffers {
   float *X[PN_MAX_LEVELS], *XP[PN_MAX_LEVELS], *Fl[PN_MAX_LEVELS], *pos[PN_MAX_LEVELS];
   float *Xlo[PN_MAX_LEVELS], *XPlo[PN_MAX_LEVELS];  // 3xTF32 low parts (tensor-core K/V projection)
@@ -458,13 +459,33 @@ static int ppn_forward(const float* query, const float* query_obj, const PnMlp3*
     S = nrm;
     O = nrm + (size_t)M * D;
   }
-  {  // row 5: importance_raw[b] = S[b] O[b]^T
+  // row 5: importance_raw[b] = S[b] O[b]^T.  >= 1024 embedding rows: tcgen05 3xTF32 pair-matrix kernel (operands split
+  // in the SM); fewer: exact-fp32 FFMA.
+  const bool tc = get_option(OPT_TENSOR_CORES) && get_option(OPT_PPN_TC) && (long long)B * N >= TC_MIN_ROWS;
+  auto pair_matrix = [&](const float* s, const float* o, float* c, int nb) -> int {
+    if (tc) return launch_pair_matrix_tc(s, o, c, nb, N, D, st);
     GemmBatch g{};
-    g.p[0] = make_linear(S, D, O, nullptr, raw, N, N, N, D);
-    g.p[0].nb = B; g.p[0].sA = (long long)N * D; g.p[0].sW = (long long)N * D; g.p[0].sC = (long long)N * N;
+    g.p[0] = make_linear(s, D, o, nullptr, c, N, N, N, D);
+    g.p[0].nb = nb; g.p[0].sA = (long long)N * D; g.p[0].sW = (long long)N * D; g.p[0].sC = (long long)N * N;
     g.count = 1;
-    PN_TRY(launch_gemm(g, st));
+    return launch_gemm(g, st);
+  };
+  const size_t img_bytes = sizeof(float) * (size_t)N * N;
+  if (!conv && raw == importance && (size_t)B * img_bytes > PPN_L2_CHUNK_BYTES) {
+    // large batches (micro-benchmark 5a): walk the batch in chunks whose pair matrices stay resident in the 126 MB
+    // L2 between the kernel that writes them and the top-k kernel that reads them back
+    int cb = (int)(PPN_L2_CHUNK_BYTES / img_bytes);
+    cb = cb < 1 ? 1 : cb;
+    for (int b0 = 0; b0 < B; b0 += cb) {
+      const int nb = B - b0 < cb ? B - b0 : cb;
+      PN_TRY(pair_matrix(S + (size_t)b0 * N * D, O + (size_t)b0 * N * D, importance + (size_t)b0 * N * N, nb));
+      PN_TRY(launch_topk_pairs(importance + (size_t)b0 * N * N, topk_idx ? topk_idx + (size_t)b0 * K : nullptr,
+                               sub_pos + (size_t)b0 * K, obj_pos + (size_t)b0 * K, query + (size_t)b0 * N * D,
+                               pair_feat ? pair_feat + (size_t)b0 * 2 * K * D : nullptr, nb, N, K, st));
+    }
+    return 0;
   }
+  PN_TRY(pair_matrix(S, O, raw, B));
   if (conv) {
     PN_TRY(launch_conv_tiny(raw, conv, importance, B, N, conv_ws, conv_bytes, st));
   } else if (raw != importance) {

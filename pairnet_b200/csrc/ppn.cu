@@ -219,39 +219,47 @@ int launch_conv_tiny(const float* x, const PnConvTiny* cv, float* y, int B, int 
 }
 
 // ------------------------------------------------------------------------------------------ top-k
-constexpr int TOPK_THREADS = 1024;
+// Row 7/8 of the hot path (pairnet_head.py:334-351): per image, the K largest entries of the N x N matrix in
+// descending order (ties: ascending flat index), idx -> (idx / N, idx % N) as int64, and the fused pair gather.
+//
+// Throughput design (one CTA per image, several CTAs per SM):
+//   1. every thread scans a strided slice of the matrix (128-bit loads) and keeps its local maximum;
+//   2. t0 = K-th largest of the THREADS local maxima.  The K largest local maxima are K distinct matrix elements
+//      >= t0, so t0 is a lower bound of the K-th largest element: { x >= t0 } contains the whole top-K.  For
+//      exchangeable data it holds only ~1.05-1.25 K elements (N = 400..100);
+//   3. the candidates are compacted into shared memory (second scan, L1/L2 hits) as 64-bit composites
+//      (order-preserving key << 32 | ~index) and ranked by counting -- the composite order IS the output order;
+//   4. adversarial inputs (more than CAND_MAX candidates, e.g. a constant matrix) fall back to an exact 4-pass
+//      radix select over the whole matrix.
 constexpr int TOPK_MAXK = 1024;
+constexpr int CAND_MAX = 2048;
 
 __device__ __forceinline__ uint32_t order_key(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ unsigned long long composite(uint32_t key, uint32_t idx) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
+}
 
-__global__ void __launch_bounds__(TOPK_THREADS) topk_pairs_kernel(const float* __restrict__ imp,
-                                                                   int64_t* __restrict__ topk_idx,
-                                                                   int64_t* __restrict__ sub_pos,
-                                                                   int64_t* __restrict__ obj_pos,
-                                                                   const float* __restrict__ query,
-                                                                   float* __restrict__ pair_feat, int N, int K) {
-  __shared__ unsigned hist[256];
-  __shared__ unsigned long long cand[TOPK_MAXK];
-  __shared__ unsigned warp_cnt[32];
-  __shared__ unsigned s_prefix, s_remaining, s_count, s_eq_taken;
-  const int b = blockIdx.x;
+// exact radix select (4 passes x 8 bits, MSB first) + ordered tie handling + bitonic sort; result in win[0..K)
+template <int THREADS>
+__device__ void radix_select_topk(const float* __restrict__ v, int NN, int K, unsigned long long* win, unsigned* hist,
+                                  unsigned* warp_cnt, unsigned* scal /* [4] */) {
   const int tid = threadIdx.x;
-  const int NN = N * N;
-  const float* v = imp + (size_t)b * NN;
-
-  // ---- exact radix select of the K-th largest key (4 passes x 8 bits, MSB first)
+  unsigned& s_prefix = scal[0];
+  unsigned& s_remaining = scal[1];
+  unsigned& s_count = scal[2];
+  unsigned& s_eq_taken = scal[3];
   if (tid == 0) { s_prefix = 0; s_remaining = (unsigned)K; }
   __syncthreads();
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    for (int i = tid; i < 256; i += TOPK_THREADS) hist[i] = 0;
+    for (int i = tid; i < 256; i += THREADS) hist[i] = 0;
     __syncthreads();
     const unsigned prefix = s_prefix;
     const unsigned pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    for (int i = tid; i < NN; i += TOPK_THREADS) {
+    for (int i = tid; i < NN; i += THREADS) {
       const uint32_t key = order_key(__ldg(v + i));
       if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
@@ -272,9 +280,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_pairs_kernel(const float* _
   const unsigned need_eq = s_remaining;   // how many elements with key == T belong to the top-K
   if (tid == 0) { s_count = 0; s_eq_taken = 0; }
   __syncthreads();
-
-  // ---- collect: keys > T in any order (sorted below), keys == T by ascending index
-  for (int base = 0; base < NN; base += TOPK_THREADS) {
+  // collect: keys > T in any order (sorted below), keys == T by ascending index
+  for (int base = 0; base < NN; base += THREADS) {
     const int i = base + tid;
     uint32_t key = 0;
     bool gt = false, eq = false;
@@ -283,11 +290,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_pairs_kernel(const float* _
       gt = key > T;
       eq = key == T;
     }
-    if (gt) {
-      const unsigned slot = atomicAdd(&s_count, 1u);
-      cand[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-    }
-    // ordered rank among equal keys
+    if (gt) win[atomicAdd(&s_count, 1u)] = composite(key, (uint32_t)i);
     const unsigned bal = __ballot_sync(0xffffffffu, eq);
     const int lane = tid & 31, wid = tid >> 5;
     if (lane == 0) warp_cnt[wid] = __popc(bal);
@@ -295,38 +298,138 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_pairs_kernel(const float* _
     unsigned before = s_eq_taken;
     for (int w2 = 0; w2 < wid; ++w2) before += warp_cnt[w2];
     const unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
-    if (eq && rank < need_eq) {
-      const unsigned slot = atomicAdd(&s_count, 1u);
-      cand[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-    }
+    if (eq && rank < need_eq) win[atomicAdd(&s_count, 1u)] = composite(key, (uint32_t)i);
     __syncthreads();
     if (tid == 0) {
       unsigned tot = 0;
-      for (int w2 = 0; w2 < TOPK_THREADS / 32; ++w2) tot += warp_cnt[w2];
+      for (int w2 = 0; w2 < THREADS / 32; ++w2) tot += warp_cnt[w2];
       s_eq_taken += tot;
     }
     __syncthreads();
   }
-  // ---- bitonic sort (descending) of the K candidates, padded with 0 (smallest)
+  // bitonic sort (descending) of the K winners, padded with 0 (smallest)
   int P = 1;
   while (P < K) P <<= 1;
-  for (int i = K + tid; i < P; i += TOPK_THREADS) cand[i] = 0ull;
+  for (int i = K + tid; i < P; i += THREADS) win[i] = 0ull;
   __syncthreads();
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < P / 2; i += TOPK_THREADS) {
+      for (int i = tid; i < P / 2; i += THREADS) {
         const int lo = 2 * i - (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
-        const unsigned long long a = cand[lo], c = cand[hi];
-        if ((a < c) == desc) { cand[lo] = c; cand[hi] = a; }
+        const unsigned long long a = win[lo], c = win[hi];
+        if ((a < c) == desc) { win[lo] = c; win[hi] = a; }
       }
       __syncthreads();
     }
   }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) topk_pairs_kernel(const float* __restrict__ imp,
+                                                             int64_t* __restrict__ topk_idx,
+                                                             int64_t* __restrict__ sub_pos,
+                                                             int64_t* __restrict__ obj_pos,
+                                                             const float* __restrict__ query,
+                                                             float* __restrict__ pair_feat, int N, int K,
+                                                             int force_radix) {
+  __shared__ uint32_t maxk[THREADS];
+  __shared__ unsigned long long cand[CAND_MAX];
+  __shared__ unsigned long long win[TOPK_MAXK];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned warp_cnt[32];
+  __shared__ unsigned scal[4];
+  __shared__ unsigned s_t0, s_ncand;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int NN = N * N;
+  const float* v = imp + (size_t)b * NN;
+  const bool vec = (NN & 3) == 0 && ((reinterpret_cast<uintptr_t>(imp) & 15) == 0);
+  const int W = vec ? 4 : 1;  // elements per thread per sweep step
+
+  // ---- 1. local maxima over a strided slice
+  uint32_t lmax = 0;
+  if (vec) {
+    for (int i = tid * 4; i < NN; i += THREADS * 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(v + i));
+      lmax = max(max(lmax, order_key(x.x)), max(order_key(x.y), max(order_key(x.z), order_key(x.w))));
+    }
+  } else {
+    for (int i = tid; i < NN; i += THREADS) lmax = max(lmax, order_key(__ldg(v + i)));
+  }
+  maxk[tid] = lmax;
+  if (tid == 0) { s_t0 = 0; s_ncand = 0; }
+  __syncthreads();
+  // ---- 2. t0 = K-th largest local maximum (rank by counting; ties broken by thread id)
+  if (K <= THREADS) {
+    unsigned cnt = 0;
+    for (int j = 0; j < THREADS; j += 4) {
+      const uint4 m = *reinterpret_cast<const uint4*>(&maxk[j]);
+      cnt += (m.x > lmax || (m.x == lmax && j < tid)) + (m.y > lmax || (m.y == lmax && j + 1 < tid)) +
+             (m.z > lmax || (m.z == lmax && j + 2 < tid)) + (m.w > lmax || (m.w == lmax && j + 3 < tid));
+    }
+    if (cnt == (unsigned)(K - 1)) s_t0 = lmax;
+  }
+  __syncthreads();
+  const uint32_t t0 = s_t0;
+  // ---- 3. compact { key >= t0 } (warp-aggregated slots; order is irrelevant, the composite carries it)
+  if (!force_radix) {
+    for (int i0 = 0; i0 < NN; i0 += THREADS * W) {
+      const int i = i0 + tid * W;
+      uint32_t key[4] = {0, 0, 0, 0};
+      bool ok[4] = {false, false, false, false};
+      if (vec) {
+        if (i < NN) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(v + i));
+          key[0] = order_key(x.x); key[1] = order_key(x.y); key[2] = order_key(x.z); key[3] = order_key(x.w);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ok[u] = key[u] >= t0;
+        }
+      } else if (i < NN) {
+        key[0] = order_key(__ldg(v + i));
+        ok[0] = key[0] >= t0;
+      }
+      const int mine = (int)ok[0] + (int)ok[1] + (int)ok[2] + (int)ok[3];
+      // warp-inclusive scan of the per-lane counts -> one atomic per warp per step
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned base = 0;
+      if (total > 0) {
+        if (lane == 31) base = atomicAdd(&s_ncand, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned slot = base + (unsigned)(incl - mine);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) {
+            if (slot < CAND_MAX) cand[slot] = composite(key[u], (uint32_t)(i + u));
+            ++slot;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned nc = s_ncand;
+  if (force_radix || nc > CAND_MAX || nc < (unsigned)K) {
+    radix_select_topk<THREADS>(v, NN, K, win, hist, warp_cnt, scal);   // ends with a barrier
+  } else {
+    // ---- 4. rank by counting: win[r] = candidate with r larger candidates
+    for (unsigned i = tid; i < nc; i += THREADS) {
+      const unsigned long long me = cand[i];
+      unsigned r = 0;
+      for (unsigned j = 0; j < nc; ++j) r += cand[j] > me;
+      if (r < (unsigned)K) win[r] = me;
+    }
+    __syncthreads();
+  }
   // ---- emit indices (pairnet_head.py:337-340)
-  for (int r = tid; r < K; r += TOPK_THREADS) {
-    const long long idx = (long long)(0xffffffffu - (uint32_t)(cand[r] & 0xffffffffull));
+  for (int r = tid; r < K; r += THREADS) {
+    const long long idx = (long long)(0xffffffffu - (uint32_t)(win[r] & 0xffffffffull));
     if (topk_idx) topk_idx[(size_t)b * K + r] = idx;
     sub_pos[(size_t)b * K + r] = idx / N;
     obj_pos[(size_t)b * K + r] = idx % N;
@@ -335,9 +438,9 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_pairs_kernel(const float* _
   if (pair_feat) {
     const float4* q4 = reinterpret_cast<const float4*>(query + (size_t)b * N * D);
     float4* p4 = reinterpret_cast<float4*>(pair_feat + (size_t)b * 2 * K * D);
-    for (int i = tid; i < 2 * K * (D / 4); i += TOPK_THREADS) {
+    for (int i = tid; i < 2 * K * (D / 4); i += THREADS) {
       const int r = i / (D / 4), c = i % (D / 4);
-      const uint32_t idx = 0xffffffffu - (uint32_t)(cand[r < K ? r : r - K] & 0xffffffffull);
+      const uint32_t idx = 0xffffffffu - (uint32_t)(win[r < K ? r : r - K] & 0xffffffffull);
       const int row = (r < K) ? (int)(idx / (uint32_t)N) : (int)(idx % (uint32_t)N);
       p4[(size_t)r * (D / 4) + c] = __ldg(q4 + (size_t)row * (D / 4) + c);
     }
@@ -350,7 +453,14 @@ int launch_topk_pairs(const float* imp, int64_t* topk_idx, int64_t* sub_pos, int
   PN_REQUIRE(K >= 1 && K <= TOPK_MAXK && (long long)K <= (long long)N * N, PN_ERR_UNSUPPORTED,
              "topk_pairs: K=%d unsupported (1..%d, <= N*N)", K, TOPK_MAXK);
   PN_REQUIRE(!pair_feat || query, PN_ERR_BAD_ARG, "topk_pairs: pair_feat needs query");
-  topk_pairs_kernel<<<B, TOPK_THREADS, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K);
+  const long long NN = (long long)N * N;
+  const int force_radix = get_option(OPT_TOPK_RADIX) != 0;
+  if (NN <= 16384)
+    topk_pairs_kernel<256><<<B, 256, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix);
+  else if (NN <= 65536)
+    topk_pairs_kernel<512><<<B, 512, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix);
+  else
+    topk_pairs_kernel<1024><<<B, 1024, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix);
   return check_launch("topk_pairs_kernel");
 }
 

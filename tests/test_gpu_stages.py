@@ -326,3 +326,79 @@ def test_group_norm_native(channels_last, relu):
                                 int(relu), int(channels_last), 1e-5, ws.data_ptr(), need,
                                 torch.cuda.current_stream().cuda_stream), "gn")
     assert rel_err(y.cpu(), ref) < 5e-6
+
+
+# --------------------------------------------------------------------------- PPN at scale (BASELINE config 5)
+@pytest.mark.parametrize("B,N", [(12, 100), (7, 200), (3, 400), (30, 37), (9, 128), (8, 130), (600, 100)])
+def test_pair_matrix_tcgen05_and_topk_batched(B, N):
+    """Pair matrix on the tcgen05 kernel (both operands split in the SM, 3-D TMA with OOB zero fill) + batched
+    top-k: importance to fp32 accuracy of the fp64 product, indices bit-exact for the matrix the kernel wrote."""
+    import torch.nn.functional as F
+    from pairnet_b200 import _native as nat, ops
+    K = 100
+    g = torch.Generator().manual_seed(1000 + N)
+    s = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    o = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    plan = ops.PpnPlan(B, N, K, "cuda")
+    assert B * N >= 1024 and nat.load().pn_get_option(7) == 1  # -> tcgen05 path
+    imp, idx, sp, op = plan.run_embeds(s.cuda(), o.cuda())
+    torch.cuda.synchronize()
+    ref = torch.matmul(s.double(), o.double().transpose(1, 2))
+    assert float((imp.cpu().double() - ref).abs().max()) < 2e-6  # |cos| <= 1: absolute = relative to the scale
+    from oracle.head import stable_topk
+    rv, ri = torch.topk(imp.cpu().flatten(1), K)
+    for b in (idx.cpu() != ri).any(1).nonzero().flatten().tolist():  # exact fp32 ties: torch's order is unspecified
+        ri[b] = torch.from_numpy(stable_topk(imp[b].flatten().cpu().numpy(), K))
+    assert torch.equal(idx.cpu(), ri)
+    assert torch.equal(sp.cpu(), torch.div(ri, N, rounding_mode="trunc"))
+    assert torch.equal(op.cpu(), torch.remainder(ri, N))
+    # the exact-FFMA pair matrix agrees to fp32 noise
+    nat.load().pn_set_option(7, 0)
+    try:
+        imp2 = plan.run_embeds(s.cuda(), o.cuda())[0].clone()
+    finally:
+        nat.load().pn_set_option(7, 1)
+    assert float((imp2 - imp).abs().max()) < 2e-6
+
+
+def test_ppn_l2_chunked_batch_equals_unchunked():
+    """Batches whose pair matrices exceed the L2 chunk budget are walked chunk by chunk: same results."""
+    import torch.nn.functional as F
+    from pairnet_b200 import ops
+    B, N, K = 1400, 100, 100   # 56 MB of pair matrices > 48 MB chunk budget
+    g = torch.Generator().manual_seed(5)
+    s = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1).cuda()
+    o = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1).cuda()
+    imp, idx, sp, op = ops.PpnPlan(B, N, K, "cuda").run_embeds(s, o)
+    ref = torch.matmul(s, o.transpose(1, 2))
+    assert float((imp - ref).abs().max()) < 5e-6
+    from oracle.head import stable_topk
+    ri = torch.topk(imp.flatten(1), K).indices
+    for b in (idx != ri).any(1).nonzero().flatten().tolist():  # exact fp32 ties: torch's order is unspecified
+        ri[b] = torch.from_numpy(stable_topk(imp[b].flatten().cpu().numpy(), K)).cuda()
+    assert torch.equal(idx, ri)
+    assert torch.equal(sp * N + op, ri)
+
+
+@pytest.mark.parametrize("N,K", [(100, 100), (100, 300), (200, 100), (400, 100), (30, 900), (16, 100)])
+def test_topk_threshold_path_equals_radix_path(N, K):
+    """Default top-k (local-maxima threshold + candidate ranking) == forced exact radix select, incl. K larger
+    than the CTA (falls back), tiny matrices, smooth (spatially correlated) and heavily tied inputs."""
+    from oracle.head import stable_topk
+    from pairnet_b200 import _native as nat, ops
+    rng = np.random.default_rng(N * 7 + K)
+    smooth = torch.from_numpy(rng.standard_normal((1, N, N)).astype(np.float32))
+    smooth = torch.nn.functional.avg_pool2d(smooth[None], 7, 1, 3)[0]
+    ramp = torch.arange(N * N, dtype=torch.float32).view(1, N, N) / (N * N)        # ascending: adversarial for blocks
+    tied = torch.from_numpy(rng.integers(0, 3, size=(1, N, N)).astype(np.float32))
+    imp = torch.cat([smooth, ramp, -ramp, tied, _t((1, N, N), 99)]).cuda()
+    a = ops.topk_pairs(imp, K)
+    nat.load().pn_set_option(6, 1)
+    try:
+        b = ops.topk_pairs(imp, K)
+    finally:
+        nat.load().pn_set_option(6, 0)
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+    for i in range(imp.shape[0]):
+        assert a[0][i].cpu().tolist() == stable_topk(imp[i].flatten().cpu().numpy(), K).tolist()
