@@ -88,6 +88,8 @@ PN_API int pn_get_option(int key);
                                  * 4-pass radix select (the fallback of the default path; parity studies) */
 #define PN_OPT_PPN_TC 7         /* default 1: pair matrix S.O^T of batches with >= 1024 embedding rows on tcgen05 (3xTF32,
                                  * operands split in the SM); 0 = exact-fp32 FFMA */
+#define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
+                                   (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */
 PN_API int pn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

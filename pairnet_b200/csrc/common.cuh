@@ -84,6 +84,8 @@ GemmProb make_linear(const float* A, int lda, const float* W, const float* bias,
 // launchers (all return 0 / error code)
 int launch_gemm(const GemmBatch& batch, cudaStream_t st);                      // B K-major
 int launch_gemm_nmajor_store(const GemmProb& p, cudaStream_t st);              // einsum, fp32 store
+bool skinny_gemm_ok(const GemmBatch& batch);                                   // skinny.cu
+int launch_skinny_gemm(const GemmBatch& batch, int maxM, int maxN, int nz, cudaStream_t st);
 int launch_gemm_nmajor_maskbits(const float* E, const float* F, uint32_t* bits, int* rowany, int B,
                                 int N, int hw, int ldf, cudaStream_t st);
 
@@ -161,7 +163,7 @@ int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
                       int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_COUNT = 8 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_COUNT = 9 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);

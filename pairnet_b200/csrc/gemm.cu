@@ -259,6 +259,8 @@ int launch_gemm(const GemmBatch& batch, cudaStream_t st) {
     PN_REQUIRE((batch.p[i].ldw & 3) == 0 && ((uintptr_t)batch.p[i].W & 15) == 0, PN_ERR_UNSUPPORTED,
                "gemm: W not 16B aligned");
   }
+  if (!big && get_option(OPT_TENSOR_CORES) && get_option(OPT_SKINNY) && skinny_gemm_ok(batch))
+    return launch_skinny_gemm(batch, maxM, maxN, nz, st);
   if (big) {
     dim3 grid(cdiv(maxN, 128), cdiv(maxM, 128), nz);
     gemm_store_kernel<128, 128, 16, 8, 8, false><<<grid, 256, 0, st>>>(batch);
