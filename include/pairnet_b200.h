@@ -100,6 +100,10 @@ PN_API int pn_sine_posenc(float* pos, int h, int w, pn_stream_t stream);
 /* mem [B,256,hw] -> x [B,hw,256] = mem^T + level_embed ; xp = x + pos */
 PN_API int pn_level_prep(const float* mem, const float* level_embed, const float* pos,
                   float* x, float* xp, int B, int hw, pn_stream_t stream);
+/* same for a token-major memory: element (b, p, c) at mem[b*batch_stride + p*256 + c] (the pixel decoder's encoder
+ * output sliced per level) -- no NCHW round trip */
+PN_API int pn_level_prep_tokens(const float* mem, long long batch_stride, const float* level_embed, const float* pos,
+                                float* x, float* xp, int B, int hw, pn_stream_t stream);
 
 /* ------------------------------------------------------------------ row 2: forward_head
  * replaces pairnet_head.py:216-258 (post_norm, cls_embed, mask_embed, einsum, bilinear, threshold) */
@@ -180,6 +184,10 @@ typedef struct {
   int h[PN_MAX_LEVELS], w[PN_MAX_LEVELS];
   const float* memory[PN_MAX_LEVELS];  /* multi_scale_memorys[l] [B,256,h,w], low -> high res */
   const float* pos[PN_MAX_LEVELS];     /* optional precomputed pn_sine_posenc tables (NULL = compute) */
+  /* memory_token_major[l] != 0: memory[l] is token-major, element (b, p, c) at memory[l][b*stride + p*256 + c] with
+   * stride = memory_batch_stride[l] (a level slice of the pixel decoder's encoder output, no NCHW copy needed) */
+  int memory_token_major[PN_MAX_LEVELS];
+  long long memory_batch_stride[PN_MAX_LEVELS];
 } PnM2FInputs;
 
 typedef struct {
@@ -268,6 +276,18 @@ PN_API size_t pn_group_norm_workspace_bytes(int B, int HW, int groups);
 PN_API int pn_group_norm(const float* x, const float* gamma, const float* beta, float* y, int B, int HW,
                          int groups, int relu, int channels_last, float eps, void* ws, size_t ws_bytes,
                          pn_stream_t stream);
+/* GroupNorm fused with the FPN top-down merge of MSDeformAttnPixelDecoder.forward:
+ *   y = GN(x) + F.interpolate(top, size=(H,W), mode="bilinear", align_corners=False)
+ * x, y channels_last [B,H*W,256] (y may alias x); top token-major: element (b, ty, tx, c) at
+ * top[b*top_batch_stride + (ty*w + tx)*256 + c] (a level slice of the encoder output). */
+PN_API int pn_gn_upsample_add(const float* x, const float* gamma, const float* beta, const float* top,
+                              long long top_batch_stride, float* y, int B, int H, int W, int h, int w, int groups,
+                              float eps, void* ws, size_t ws_bytes, pn_stream_t stream);
+/* 1x1 convolution of a channels_last map [B,HW,256] into an NCHW-contiguous map [B,cout,HW] (mask_feature):
+ * tcgen05 3xTF32 GEMM with the activations split in the SM and a transposed store. */
+PN_API size_t pn_conv1x1_nhwc_to_nchw_workspace_bytes(int cout);
+PN_API int pn_conv1x1_nhwc_to_nchw(const float* x, const float* w, const float* bias, float* y, int B, int HW,
+                                   int cout, void* ws, size_t ws_bytes, pn_stream_t stream);
 /* sampling core only: value [B,nq,256], ol [B*nq, 8*L*P*3] (offsets then attention logits) -> out [B*nq,256] */
 PN_API int pn_msda_sample(const float* value, const float* ol, float* out, const int* h, const int* w_,
                           int num_levels, int num_points, int B, pn_stream_t stream);

@@ -51,7 +51,8 @@ class PnM2FWeights(C.Structure):
 class PnM2FInputs(C.Structure):
     _fields_ = [("B", C.c_int), ("H4", C.c_int), ("W4", C.c_int), ("mask_features", c_void_p),
                 ("h", C.c_int * PN_MAX_LEVELS), ("w", C.c_int * PN_MAX_LEVELS),
-                ("memory", c_void_p * PN_MAX_LEVELS), ("pos", c_void_p * PN_MAX_LEVELS)]
+                ("memory", c_void_p * PN_MAX_LEVELS), ("pos", c_void_p * PN_MAX_LEVELS),
+                ("memory_token_major", C.c_int * PN_MAX_LEVELS), ("memory_batch_stride", C.c_longlong * PN_MAX_LEVELS)]
 
 
 class PnM2FOutputs(C.Structure):
@@ -101,6 +102,7 @@ SIGNATURES = {
     "pn_device_info": (i32, [P(i32), P(i32), P(i32)]),
     "pn_sine_posenc": (i32, [vp, i32, i32, vp]),
     "pn_level_prep": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "pn_level_prep_tokens": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, vp]),
     "pn_mask_feature_resize": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "pn_attn_mask_bits": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "pn_mask_pred": (i32, [vp, vp, vp, i32, i32, i32, vp]),
@@ -129,6 +131,9 @@ SIGNATURES = {
     "pn_msda_encoder_forward": (i32, [P(PnMsdaEncoderWeights), vp, vp, P(i32), P(i32), vp, i32, vp, sz, vp]),
     "pn_group_norm_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_group_norm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, sz, vp]),
+    "pn_gn_upsample_add": (i32, [vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, C.c_float, vp, sz, vp]),
+    "pn_conv1x1_nhwc_to_nchw_workspace_bytes": (sz, [i32]),
+    "pn_conv1x1_nhwc_to_nchw": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
     "pn_msda_sample": (i32, [vp, vp, vp, P(i32), P(i32), i32, i32, i32, vp]),
     "pn_head_workspace_bytes": (sz, [P(PnHeadWeights), P(PnM2FInputs)]),
     "pn_head_forward": (i32, [P(PnHeadWeights), P(PnM2FInputs), P(PnHeadOutputs), vp, sz, vp]),

@@ -301,8 +301,13 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     // X / XP as A operands only when the GEMM does not split A in-kernel
     const bool x_split = tc && (get_option(OPT_FA_TC) || !raw_a);
     const bool xp_split = tc && !raw_a;
-    PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st,
-                             x_split ? b.Xlo[l] : nullptr, xp_split ? b.XPlo[l] : nullptr));
+    if (in->memory_token_major[l])
+      PN_TRY(launch_level_prep_tokens(in->memory[l], in->memory_batch_stride[l], w->level_embed + (size_t)l * D, pos,
+                                      b.X[l], b.XP[l], p.B, p.hw[l], st, x_split ? b.Xlo[l] : nullptr,
+                                      xp_split ? b.XPlo[l] : nullptr));
+    else
+      PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st,
+                               x_split ? b.Xlo[l] : nullptr, xp_split ? b.XPlo[l] : nullptr));
     PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
                                       st));
   }
@@ -588,6 +593,11 @@ int pn_sine_posenc(float* pos, int h, int w, pn_stream_t stream) { return launch
 int pn_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp, int B, int hw,
                   pn_stream_t stream) {
   return launch_level_prep(mem, level_embed, pos, x, xp, B, hw, as_stream(stream));
+}
+
+int pn_level_prep_tokens(const float* mem, long long batch_stride, const float* level_embed, const float* pos, float* x,
+                         float* xp, int B, int hw, pn_stream_t stream) {
+  return launch_level_prep_tokens(mem, batch_stride, level_embed, pos, x, xp, B, hw, as_stream(stream));
 }
 
 int pn_mask_feature_resize(const float* mask_feature, float* out, int B, int H, int W, int h, int w, int ldo,

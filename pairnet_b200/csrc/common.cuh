@@ -162,6 +162,8 @@ constexpr float ATTN_QSCALE = 0.17677669529663687f * 1.4426950408889634f;  // (1
 int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
                       int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
+int launch_level_prep_tokens(const float* mem, long long bstride, const float* level_embed, const float* pos, float* x,
+                             float* xp, int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
 enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_COUNT = 9 };
 int get_option(int key);

@@ -7,6 +7,7 @@
 namespace pn {
 
 constexpr int GN_THREADS = 256;
+constexpr int GN_NCHUNK = 148;  // statistics CTAs per image (x B images: >= one wave of the 148 SMs)
 
 // ---- pass 1: per-CTA partial (sum, sumsq) per (b, group), fp32 per thread -> double per CTA ---------------
 // NHWC: x[b][p][c]; CTA covers `ppc` pixels; thread t: channel quad (t % 64) * 4, pixel lane t / 64.
@@ -94,6 +95,42 @@ __global__ void __launch_bounds__(256) gn_apply_nhwc_kernel(const float* __restr
   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
   reinterpret_cast<float4*>(y)[i] = o;
 }
+// FPN top-down merge fused into the apply pass (mmdet MSDeformAttnPixelDecoder.forward:
+//   y = lateral_conv(x) [conv -> GN]  +  F.interpolate(top, size=(H,W), mode="bilinear", align_corners=False)):
+// x, y NHWC [B,H*W,256]; top token-major [b * top_bstride + (ty*w + tx) * 256 + c].  Same arithmetic order as
+// ATen's upsample_bilinear2d (h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)).
+__global__ void __launch_bounds__(256) gn_apply_upadd_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ ss,
+                                                                   const float* __restrict__ top, long long top_bstride,
+                                                                   float* __restrict__ y, long long n4, int H, int W, int h,
+                                                                   int w, float sh, float sw) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // float4 index over [B,H*W,64]
+  if (i >= n4) return;
+  const int cq = (int)(i & 63);
+  const long long pix = i >> 6;
+  const int HW = H * W;
+  const int b = (int)(pix / HW), p = (int)(pix - (long long)b * HW);
+  const int oy = p / W, ox = p - oy * W;
+  float sy = sh * ((float)oy + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  float sx = sw * ((float)ox + 0.5f) - 0.5f;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int yp = (y0 < h - 1) ? 1 : 0, xq = (x0 < w - 1) ? 1 : 0;
+  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+  const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+  const float4* tb = reinterpret_cast<const float4*>(top + (size_t)b * top_bstride) + cq;
+  const float4 v00 = __ldg(tb + (size_t)(y0 * w + x0) * 64), v01 = __ldg(tb + (size_t)(y0 * w + x0 + xq) * 64);
+  const float4 v10 = __ldg(tb + (size_t)((y0 + yp) * w + x0) * 64), v11 = __ldg(tb + (size_t)((y0 + yp) * w + x0 + xq) * 64);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(ss) + ((size_t)b * D + cq * 4) / 2);
+  const float4 s1 = __ldg(reinterpret_cast<const float4*>(ss) + ((size_t)b * D + cq * 4) / 2 + 1);
+  float4 o;
+  o.x = fmaf(v.x, s0.x, s0.y) + (ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x));
+  o.y = fmaf(v.y, s0.z, s0.w) + (ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y));
+  o.z = fmaf(v.z, s1.x, s1.y) + (ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z));
+  o.w = fmaf(v.w, s1.z, s1.w) + (ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w));
+  reinterpret_cast<float4*>(y)[i] = o;
+}
 __global__ void __launch_bounds__(256) gn_apply_nchw_kernel(const float* __restrict__ x, const float* __restrict__ ss,
                                                              float* __restrict__ y, int HW, int relu) {
   const int bc = blockIdx.y;  // b*256 + c
@@ -113,7 +150,7 @@ using namespace pn;
 extern "C" {
 
 size_t pn_group_norm_workspace_bytes(int B, int HW, int groups) {
-  const int nchunk = 64;
+  const int nchunk = GN_NCHUNK;
   return (size_t)B * groups * nchunk * 2 * sizeof(double) + (size_t)B * D * 2 * sizeof(float) + 512;
 }
 
@@ -125,7 +162,7 @@ int pn_group_norm(const float* x, const float* gamma, const float* beta, float* 
   PN_REQUIRE(ws_bytes >= pn_group_norm_workspace_bytes(B, HW, groups), PN_ERR_WORKSPACE, "group_norm: workspace too small");
   PN_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, PN_ERR_UNSUPPORTED, "group_norm: 16B alignment");
   cudaStream_t st = as_stream(stream);
-  const int nchunk = 64;
+  const int nchunk = GN_NCHUNK;
   double* part = reinterpret_cast<double*>(wsp);
   float* ss = reinterpret_cast<float*>(part + (size_t)B * groups * nchunk * 2);
   const double count = (double)HW * (D / groups);
@@ -148,6 +185,52 @@ int pn_group_norm(const float* x, const float* gamma, const float* beta, float* 
   gx = gx < 1 ? 1 : gx;
   gn_apply_nchw_kernel<<<dim3(gx, B * D), 256, 0, st>>>(x, ss, y, HW, relu);
   return check_launch("gn_apply_nchw_kernel");
+}
+
+
+/* GroupNorm fused with the FPN top-down merge:  y = GN(x) + bilinear_upsample(top)  (channels_last x / y) */
+int pn_gn_upsample_add(const float* x, const float* gamma, const float* beta, const float* top,
+                       long long top_batch_stride, float* y, int B, int H, int W, int h, int w, int groups, float eps,
+                       void* wsp, size_t ws_bytes, pn_stream_t stream) {
+  PN_REQUIRE(x && gamma && beta && top && y && wsp, PN_ERR_BAD_ARG, "gn_upsample_add: null argument");
+  PN_REQUIRE(B > 0 && H > 0 && W > 0 && h > 0 && w > 0, PN_ERR_BAD_ARG, "gn_upsample_add: bad sizes");
+  PN_REQUIRE(groups > 0 && groups <= 64 && D % groups == 0 && (D / groups) % 4 == 0, PN_ERR_UNSUPPORTED,
+             "gn_upsample_add: 256 channels, groups must divide 64");
+  const int HW = H * W;
+  PN_REQUIRE(ws_bytes >= pn_group_norm_workspace_bytes(B, HW, groups), PN_ERR_WORKSPACE,
+             "gn_upsample_add: workspace too small");
+  PN_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)top) & 15) == 0 && top_batch_stride % 4 == 0,
+             PN_ERR_UNSUPPORTED, "gn_upsample_add: 16B alignment");
+  cudaStream_t st = as_stream(stream);
+  const int nchunk = GN_NCHUNK;
+  double* part = reinterpret_cast<double*>(wsp);
+  float* ss = reinterpret_cast<float*>(part + (size_t)B * groups * nchunk * 2);
+  gn_stats_nhwc_kernel<<<dim3(nchunk, B), GN_THREADS, 0, st>>>(x, part, HW, cdiv(HW, nchunk), groups, nchunk);
+  PN_TRY(check_launch("gn_stats_nhwc_kernel"));
+  gn_finalize_kernel<<<B, D, 0, st>>>(part, gamma, beta, ss, groups, nchunk, (double)HW * (D / groups), eps);
+  PN_TRY(check_launch("gn_finalize_kernel"));
+  const long long n4 = (long long)B * HW * (D / 4);
+  gn_apply_upadd_nhwc_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, ss, top, top_batch_stride, y, n4, H, W, h, w,
+                                                            (float)h / (float)H, (float)w / (float)W);
+  return check_launch("gn_apply_upadd_nhwc_kernel");
+}
+
+/* 1x1 convolution of a channels_last map into an NCHW-contiguous map (mask_feature of the pixel decoder):
+ * y[b][n][p] = sum_k x[b][p][k] w[n][k] + bias[n];  tcgen05 3xTF32 GEMM, activations split in the SM, transposed store. */
+size_t pn_conv1x1_nhwc_to_nchw_workspace_bytes(int cout) { return (size_t)2 * cout * D * sizeof(float) + 512; }
+int pn_conv1x1_nhwc_to_nchw(const float* x, const float* w, const float* bias, float* y, int B, int HW, int cout,
+                            void* wsp, size_t ws_bytes, pn_stream_t stream) {
+  PN_REQUIRE(x && w && y && wsp && B > 0 && HW > 0 && cout > 0, PN_ERR_BAD_ARG, "conv1x1: bad args");
+  PN_REQUIRE(ws_bytes >= pn_conv1x1_nhwc_to_nchw_workspace_bytes(cout), PN_ERR_WORKSPACE, "conv1x1: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  Workspace ws(wsp, ws_bytes);
+  float* wh = ws.take<float>((size_t)cout * D);
+  float* wl = ws.take<float>((size_t)cout * D);
+  PN_TRY(launch_split_tf32(w, wh, wl, (size_t)cout * D, st));
+  UmmaOperand o{x, nullptr, D, wh, wl, D, bias, y, HW, B * HW, cout, D};
+  o.a_is_raw = 1;
+  o.t_rows = HW;
+  return launch_umma_gemm(&o, 1, 3, st);
 }
 
 }  // extern "C"

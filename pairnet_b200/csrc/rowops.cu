@@ -246,6 +246,45 @@ __global__ void __launch_bounds__(256) level_prep_kernel(const float* __restrict
     }
   }
 }
+// token-major source (a level slice of the pixel decoder's encoder output): no transpose, 128-bit elementwise
+__global__ void __launch_bounds__(256) level_prep_tokens_kernel(const float* __restrict__ mem, long long bstride,
+                                                                 const float* __restrict__ level_embed,
+                                                                 const float* __restrict__ pos, float* __restrict__ x,
+                                                                 float* __restrict__ xp, float* __restrict__ x_lo,
+                                                                 float* __restrict__ xp_lo, int hw, long long n4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // float4 index over [B,hw,64]
+  if (i >= n4) return;
+  const int cq = (int)(i & 63);
+  const long long tok = i >> 6;
+  const int b = (int)(tok / hw), p = (int)(tok - (long long)b * hw);
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mem + (size_t)b * bstride + (size_t)p * D) + cq);
+  const float4 le = __ldg(reinterpret_cast<const float4*>(level_embed) + cq);
+  const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + (size_t)p * D) + cq);
+  const float v[4] = {m.x + le.x, m.y + le.y, m.z + le.z, m.w + le.w};
+  const float vp[4] = {v[0] + ps.x, v[1] + ps.y, v[2] + ps.z, v[3] + ps.w};
+  float a[4], al[4], c[4], cl[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    a[u] = x_lo ? rna_tf32f(v[u]) : v[u];
+    al[u] = x_lo ? rna_tf32f(v[u] - a[u]) : 0.f;
+    c[u] = xp_lo ? rna_tf32f(vp[u]) : vp[u];
+    cl[u] = xp_lo ? rna_tf32f(vp[u] - c[u]) : 0.f;
+  }
+  reinterpret_cast<float4*>(x)[i] = make_float4(a[0], a[1], a[2], a[3]);
+  reinterpret_cast<float4*>(xp)[i] = make_float4(c[0], c[1], c[2], c[3]);
+  if (x_lo) reinterpret_cast<float4*>(x_lo)[i] = make_float4(al[0], al[1], al[2], al[3]);
+  if (xp_lo) reinterpret_cast<float4*>(xp_lo)[i] = make_float4(cl[0], cl[1], cl[2], cl[3]);
+}
+int launch_level_prep_tokens(const float* mem, long long bstride, const float* level_embed, const float* pos, float* x,
+                             float* xp, int B, int hw, cudaStream_t st, float* x_lo, float* xp_lo) {
+  PN_REQUIRE(mem && level_embed && pos && x && xp && B > 0 && hw > 0, PN_ERR_BAD_ARG, "level_prep: bad args");
+  PN_REQUIRE(((uintptr_t)mem & 15) == 0 && bstride % 4 == 0 && bstride >= (long long)hw * D, PN_ERR_UNSUPPORTED,
+             "level_prep: token-major memory must be 16B aligned with a batch stride >= hw*256");
+  const long long n4 = (long long)B * hw * (D / 4);
+  level_prep_tokens_kernel<<<cdiv(n4, 256), 256, 0, st>>>(mem, bstride, level_embed, pos, x, xp, x_lo, xp_lo, hw, n4);
+  return check_launch("level_prep_tokens_kernel");
+}
+
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp, int B,
                       int hw, cudaStream_t st, float* x_lo, float* xp_lo) {
   PN_REQUIRE(mem && level_embed && pos && x && xp && B > 0 && hw > 0, PN_ERR_BAD_ARG, "level_prep: bad args");

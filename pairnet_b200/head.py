@@ -244,7 +244,7 @@ class CrossHead2(nn.Module):
             raise nat.NativeError("CrossHead2.forward needs CUDA tensors on a B200; there is no CPU fallback")
         stream = torch.cuda.current_stream(dev).cuda_stream
         mask_features = mask_features.float().contiguous()
-        memorys = [m.float().contiguous() for m in memorys]
+        memorys = [m.float() for m in memorys]
         B, Cc, H4, W4 = mask_features.shape
         assert Cc == nat.EMBED_DIMS and len(memorys) == self.num_transformer_feat_level
         N, R, K = self.num_queries, self.num_rel_query, self.num_rel_query
@@ -254,7 +254,16 @@ class CrossHead2(nn.Module):
         inp.B, inp.H4, inp.W4, inp.mask_features = B, H4, W4, mask_features.data_ptr()
         keep = []
         for l, m in enumerate(memorys):
-            inp.h[l], inp.w[l], inp.memory[l] = m.shape[2], m.shape[3], m.data_ptr()
+            # the pixel decoder hands out NCHW *views* of its token-major encoder output ([B,nq,256] sliced per
+            # level): consume them in place instead of materialising an NCHW copy that level prep would transpose back
+            hl, wl = m.shape[2], m.shape[3]
+            if (not m.is_contiguous() and m.stride(1) == 1 and m.stride(3) == Cc and m.stride(2) == wl * Cc
+                    and m.stride(0) >= hl * wl * Cc and m.stride(0) % 4 == 0 and m.data_ptr() % 16 == 0):
+                inp.memory_token_major[l], inp.memory_batch_stride[l] = 1, m.stride(0)
+            else:
+                m = m.contiguous()
+            keep.append(m)
+            inp.h[l], inp.w[l], inp.memory[l] = hl, wl, m.data_ptr()
             pt = self._pos_table(m.shape[2], m.shape[3], dev, stream)
             inp.pos[l] = pt.data_ptr()
             keep.append(pt)

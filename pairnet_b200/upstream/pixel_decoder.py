@@ -178,6 +178,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         # encoder implementation on CUDA tensors: "native" = pn_msda_encoder_forward (tcgen05 GEMMs + hand-written
         # deformable sampling); "torch" = the PyTorch/grid_sample restatement below (kept for A/B tests)
         self.encoder_impl = "native"
+        self.tail_impl = "native"  # FPN merge + mask_feature on the CUDA library ("torch" = cuDNN/ATen restatement)
         self._enc_key = None
         self._enc_struct = None
         self._enc_ws = None
@@ -285,8 +286,62 @@ class MSDeformAttnPixelDecoder(nn.Module):
         for h, w in shapes:
             outs.append(mem[:, :, start:start + h * w].reshape(B, -1, h, w))
             start += h * w
+        native = x.is_cuda and not torch.is_grad_enabled() and self.tail_impl == "native"
         for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
-            cur = self.lateral_convs[i](feats[i])
-            y = cur + F.interpolate(outs[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
+            y = self._native_lateral_merge(self.lateral_convs[i], feats[i], outs[-1]) if native else None
+            if y is None:
+                cur = self.lateral_convs[i](feats[i])
+                y = cur + F.interpolate(outs[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
             outs.append(self.output_convs[i](y))
-        return self.mask_feature(outs[-1]), outs[: self.num_outs]
+        mf = self._native_mask_feature(outs[-1]) if native else None
+        if mf is None:
+            mf = self.mask_feature(outs[-1])
+        return mf, outs[: self.num_outs]
+
+    # ---- FPN tail on the CUDA library (channels_last maps): GN fused with the bilinear top-down merge, and the
+    #      mask_feature 1x1 convolution as a tcgen05 GEMM that stores NCHW directly (what the hot path consumes)
+    def _scratch(self, name, nbytes, device):
+        ws = self.__dict__.get(name)
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.__dict__[name] = ws
+        return ws
+
+    @staticmethod
+    def _is_nhwc(t):
+        B, Cc, H, W = t.shape
+        return (t.dtype == torch.float32 and Cc == nat.EMBED_DIMS and t.stride(1) == 1 and t.stride(3) == Cc
+                and t.stride(2) == W * Cc and t.stride(0) >= H * W * Cc and t.stride(0) % 4 == 0
+                and t.data_ptr() % 16 == 0)
+
+    def _native_lateral_merge(self, lat, feat, top):
+        cur = lat.conv(feat)
+        if not (self._is_nhwc(cur) and cur.stride(0) == cur.shape[2] * cur.shape[3] * cur.shape[1]
+                and self._is_nhwc(top) and not lat.with_act):
+            return None
+        lib = nat.load()
+        B, _, H, W = cur.shape
+        h, w = top.shape[-2:]
+        ws = self._scratch("_gn_ws", lib.pn_group_norm_workspace_bytes(B, H * W, lat.gn.num_groups), cur.device)
+        nat.check(lib.pn_gn_upsample_add(cur.data_ptr(), lat.gn.weight.data_ptr(), lat.gn.bias.data_ptr(),
+                                         top.data_ptr(), top.stride(0), cur.data_ptr(), B, H, W, h, w,
+                                         lat.gn.num_groups, lat.gn.eps, ws.data_ptr(), ws.numel(),
+                                         torch.cuda.current_stream(cur.device).cuda_stream), "pn_gn_upsample_add")
+        return cur
+
+    def _native_mask_feature(self, x):
+        conv = self.mask_feature
+        B, Cc, H, W = x.shape
+        if not (self._is_nhwc(x) and x.stride(0) == H * W * Cc and conv.kernel_size == (1, 1)
+                and conv.in_channels == nat.EMBED_DIMS and conv.out_channels % 128 == 0 and (H * W) % 4 == 0):
+            return None
+        lib = nat.load()
+        cout = conv.out_channels
+        ws = self._scratch("_mf_ws", lib.pn_conv1x1_nhwc_to_nchw_workspace_bytes(cout), x.device)
+        y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
+        nat.check(lib.pn_conv1x1_nhwc_to_nchw(x.data_ptr(), conv.weight.data_ptr(),
+                                              conv.bias.data_ptr() if conv.bias is not None else None, y.data_ptr(),
+                                              B, H * W, cout, ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream(x.device).cuda_stream),
+                  "pn_conv1x1_nhwc_to_nchw")
+        return y

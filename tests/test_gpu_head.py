@@ -197,6 +197,29 @@ def test_detector_end_to_end_small_image():
     assert model.bbox_head.last_launch_count > 100
 
 
+def test_token_major_memories_equal_nchw_memories(heads):
+    """The head consumes the pixel decoder's token-major level slices in place; results are bit-identical to the
+    NCHW-contiguous inputs of the reference signature."""
+    from oracle.make_golden import small_head_inputs
+    o, p = heads
+    mf, mems = small_head_inputs(2, (32, 48), 91)
+    mems_c = [m.cuda().contiguous() for m in mems]
+    nq = sum(m.shape[2] * m.shape[3] for m in mems)
+    enc = torch.empty((2, nq, 256), device="cuda")
+    views, start = [], 0
+    for m in mems_c:
+        h, w = m.shape[2:]
+        enc[:, start:start + h * w] = m.flatten(2).transpose(1, 2)
+        views.append(enc.transpose(1, 2)[:, :, start:start + h * w].reshape(2, 256, h, w))
+        start += h * w
+    assert not views[0].is_contiguous()
+    cls_a, msk_a = p.forward_from_memories(mf.cuda(), mems_c)
+    a = {k: v.clone() for k, v in {**cls_a, **msk_a}.items()}
+    cls_b, msk_b = p.forward_from_memories(mf.cuda(), views)
+    for k, v in {**cls_b, **msk_b}.items():
+        assert torch.equal(a[k], v), k
+
+
 @pytest.mark.parametrize("N,R,B,hw4", [(200, 200, 1, (32, 32)), (100, 100, 3, (24, 40)), (50, 30, 2, (16, 24))])
 def test_head_other_query_counts_and_batches(N, R, B, hw4):
     """CrossHead2 is N-generic (BASELINE config 4 uses 200 queries): build both implementations with

@@ -328,6 +328,82 @@ def test_group_norm_native(channels_last, relu):
     assert rel_err(y.cpu(), ref) < 5e-6
 
 
+def test_level_prep_tokens_bit_exact_with_nchw_path():
+    """token-major memories (level slices of the encoder output, batch stride > hw*256) give the same X / XP bits."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    B, h, w, nq = 2, 9, 13, 9 * 13 + 40
+    enc = _t((B, nq, 256), 61).cuda()                      # [B,nq,256]; the level starts at token 24
+    tok = enc[:, 24:24 + h * w]                           # strided view, batch stride nq*256
+    lvl, pos = _t((256,), 62).cuda(), _t((h * w, 256), 63).cuda()
+    x, xp = torch.empty((B, h * w, 256), device="cuda"), torch.empty((B, h * w, 256), device="cuda")
+    nat.check(lib.pn_level_prep_tokens(tok.data_ptr(), tok.stride(0), lvl.data_ptr(), pos.data_ptr(), x.data_ptr(),
+                                       xp.data_ptr(), B, h * w, torch.cuda.current_stream().cuda_stream), "lp")
+    rx = tok + lvl.view(1, 1, -1)
+    assert torch.equal(x, rx)
+    assert torch.equal(xp, rx + pos[None])
+
+
+@pytest.mark.parametrize("H,W,h,w", [(40, 56, 20, 28), (50, 84, 25, 42), (37, 53, 19, 27)])
+def test_gn_upsample_add(H, W, h, w):
+    """FPN merge: GN(lateral) + bilinear_up(top), top token-major with a batch stride (mmdet pixel decoder forward)."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    B = 2
+    x = _t((B, 256, H, W), 64, 3.0) + 0.5
+    g, b = _t((256,), 65), _t((256,), 66)
+    enc = _t((B, h * w + 11, 256), 67)
+    top = enc[:, 11:].transpose(1, 2).reshape(B, 256, h, w)
+    ref = F.group_norm(x.double(), 32, g.double(), b.double(), 1e-5) + F.interpolate(
+        top.double(), size=(H, W), mode="bilinear", align_corners=False)
+    ref32 = F.group_norm(x, 32, g, b, 1e-5) + F.interpolate(top, size=(H, W), mode="bilinear", align_corners=False)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    encc, gc, bc = enc.cuda(), g.cuda(), b.cuda()
+    topc = encc[:, 11:]
+    need = lib.pn_group_norm_workspace_bytes(B, H * W, 32)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    nat.check(lib.pn_gn_upsample_add(xc.data_ptr(), gc.data_ptr(), bc.data_ptr(), topc.data_ptr(), topc.stride(0),
+                                     xc.data_ptr(), B, H, W, h, w, 32, 1e-5, ws.data_ptr(), need,
+                                     torch.cuda.current_stream().cuda_stream), "gn_upadd")
+    assert rel_err(xc.cpu(), ref) < 5e-6
+    assert rel_err(xc.cpu(), ref32) < 5e-6
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 40, 56), (1, 13, 20), (3, 25, 44)])
+def test_conv1x1_nhwc_to_nchw(B, H, W):
+    """mask_feature 1x1 conv as a tcgen05 3xTF32 GEMM with a transposed (NCHW) store: fp32-level accuracy."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    x, wt, bias = _t((B, 256, H, W), 68), _t((256, 256, 1, 1), 69, 0.1), _t((256,), 70)
+    ref = F.conv2d(x.double(), wt.double(), bias.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    wc, bc = wt.cuda(), bias.cuda()
+    need = lib.pn_conv1x1_nhwc_to_nchw_workspace_bytes(256)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    y = torch.empty((B, 256, H, W), device="cuda")
+    nat.check(lib.pn_conv1x1_nhwc_to_nchw(xc.data_ptr(), wc.data_ptr(), bc.data_ptr(), y.data_ptr(), B, H * W, 256,
+                                          ws.data_ptr(), need, torch.cuda.current_stream().cuda_stream), "conv1x1")
+    assert rel_err(y.cpu(), ref) < 5e-6
+
+
+def test_pixel_decoder_native_tail_vs_torch():
+    """FPN tail on the CUDA library vs the cuDNN/ATen restatement (same device, same encoder output)."""
+    m = _pixel_decoder()
+    feats = [_t((2, 256, 40, 56), 41).cuda().contiguous(memory_format=torch.channels_last),
+             _t((2, 512, 20, 28), 42).cuda().contiguous(memory_format=torch.channels_last),
+             _t((2, 1024, 10, 14), 43).cuda().contiguous(memory_format=torch.channels_last),
+             _t((2, 2048, 5, 7), 44).cuda().contiguous(memory_format=torch.channels_last)]
+    with torch.no_grad():
+        m.tail_impl = "native"
+        mf_n, mem_n = m(feats)
+        m.tail_impl = "torch"
+        mf_t, mem_t = m(feats)
+    assert mf_n.is_contiguous() and mf_n.shape == mf_t.shape
+    for a, b in zip(mem_n, mem_t):
+        assert torch.equal(a, b)
+    assert rel_err(mf_n, mf_t) < 1e-3  # the 3x3 output conv (cuDNN, TF32) is shared; the 1x1 is fp32-accurate here
+
+
 # --------------------------------------------------------------------------- PPN at scale (BASELINE config 5)
 @pytest.mark.parametrize("B,N", [(12, 100), (7, 200), (3, 400), (30, 37), (9, 128), (8, 130), (600, 100)])
 def test_pair_matrix_tcgen05_and_topk_batched(B, N):
