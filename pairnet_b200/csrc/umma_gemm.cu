@@ -257,6 +257,21 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
           // transposed store: lanes hold consecutive rows -> each column is one coalesced 128-byte store
           const int bi = row / P.t_rows, r = row - bi * P.t_rows;
           const float* bias_c = bias_t + c0;
+          if (!P.C_lo && !P.relu && !P.bias_per_row && n0 + c0 + 32 <= P.N) {
+            // fast path (full chunk, plain store): one FADD + one STG per element, pointer bumped by the row pitch
+            float* dst = P.C + ((size_t)bi * P.N + n0 + c0) * P.ldc + r;
+            const size_t pitch = (size_t)P.ldc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias_c + j);
+              dst[0] = __uint_as_float(v[j]) + bb.x;
+              dst[pitch] = __uint_as_float(v[j + 1]) + bb.y;
+              dst[2 * pitch] = __uint_as_float(v[j + 2]) + bb.z;
+              dst[3 * pitch] = __uint_as_float(v[j + 3]) + bb.w;
+              dst += 4 * pitch;
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
