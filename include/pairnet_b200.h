@@ -88,6 +88,8 @@ PN_API int pn_get_option(int key);
                                  * 4-pass radix select (the fallback of the default path; parity studies) */
 #define PN_OPT_PPN_TC 7         /* default 1: pair matrix S.O^T of batches with >= 1024 embedding rows on tcgen05 (3xTF32,
                                  * operands split in the SM); 0 = exact-fp32 FFMA */
+#define PN_OPT_MASK_TC 9        /* default 1: mask einsums (attention-mask bits, final mask_pred) on the tcgen05 GEMM with
+                                   token-major operands; 0 = FFMA kernels on NCHW / N-major operands */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */
@@ -120,6 +122,18 @@ PN_API int pn_attn_mask_bits(const float* E, const float* F, uint32_t* bits, int
 /* mask_pred [B,N,HW] = E [B,N,256] . F [B,256,HW]   (the einsum "bqc,bchw->bqhw") */
 PN_API int pn_mask_pred(const float* E, const float* F, float* mask_pred, int B, int N, int HW,
                  pn_stream_t stream);
+/* tensor-core variants on token-major operands (F_tokens [B,hw,256]; E [B,N,256], N <= 256):
+ * tcgen05 3xTF32 GEMM with keys / pixels as the M tiles; sign + warp-ballot epilogue (bits) or transposed store (pred).
+ * bits / rowany as in pn_attn_mask_bits (rowany must be zeroed by the caller), words >= ceil(hw/32). */
+PN_API int pn_mask_feature_resize_tokens(const float* mask_feature_tokens /* [B,H*W,256] */, float* out /* [B,h*w,256] */,
+                                         int B, int H, int W, int h, int w, pn_stream_t stream);
+PN_API int pn_nchw_to_tokens(const float* src /* [B,256,HW] */, float* dst /* [B,HW,256] */, int B, int HW,
+                             pn_stream_t stream);
+PN_API size_t pn_mask_tc_workspace_bytes(int B, int N);
+PN_API int pn_attn_mask_bits_tc(const float* E, const float* F_tokens, uint32_t* bits, int* rowany, int B, int N, int hw,
+                                int words, void* ws, size_t ws_bytes, pn_stream_t stream);
+PN_API int pn_mask_pred_tc(const float* E, const float* F_tokens, float* mask_pred /* [B,N,HW] */, int B, int N, int HW,
+                           void* ws, size_t ws_bytes, pn_stream_t stream);
 
 /* ------------------------------------------------------------------ generic bricks */
 /* y[M,N] = act(x[M,K] W[N,K]^T + b) (+ resid[M,N]);  relu: 0/1 */
@@ -188,6 +202,8 @@ typedef struct {
    * stride = memory_batch_stride[l] (a level slice of the pixel decoder's encoder output, no NCHW copy needed) */
   int memory_token_major[PN_MAX_LEVELS];
   long long memory_batch_stride[PN_MAX_LEVELS];
+  /* != 0: mask_features is token-major [B,H4*W4,256] (a channels_last map); needs PN_OPT_MASK_TC */
+  int mask_features_token_major;
 } PnM2FInputs;
 
 typedef struct {

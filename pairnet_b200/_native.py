@@ -52,7 +52,8 @@ class PnM2FInputs(C.Structure):
     _fields_ = [("B", C.c_int), ("H4", C.c_int), ("W4", C.c_int), ("mask_features", c_void_p),
                 ("h", C.c_int * PN_MAX_LEVELS), ("w", C.c_int * PN_MAX_LEVELS),
                 ("memory", c_void_p * PN_MAX_LEVELS), ("pos", c_void_p * PN_MAX_LEVELS),
-                ("memory_token_major", C.c_int * PN_MAX_LEVELS), ("memory_batch_stride", C.c_longlong * PN_MAX_LEVELS)]
+                ("memory_token_major", C.c_int * PN_MAX_LEVELS), ("memory_batch_stride", C.c_longlong * PN_MAX_LEVELS),
+                ("mask_features_token_major", C.c_int)]
 
 
 class PnM2FOutputs(C.Structure):
@@ -93,6 +94,8 @@ i32, i64, sz, vp = C.c_int, C.c_longlong, C.c_size_t, c_void_p
 P = C.POINTER
 
 # name -> (restype, argtypes); every symbol declared in include/pairnet_b200.h
+PN_OPT_TENSOR_CORES, PN_OPT_OVERLAP, PN_OPT_SKINNY, PN_OPT_MASK_TC = 0, 3, 8, 9  # include/pairnet_b200.h
+
 SIGNATURES = {
     "pn_version": (i32, []),
     "pn_last_error_string": (C.c_char_p, []),
@@ -106,6 +109,11 @@ SIGNATURES = {
     "pn_mask_feature_resize": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "pn_attn_mask_bits": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "pn_mask_pred": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "pn_mask_feature_resize_tokens": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "pn_nchw_to_tokens": (i32, [vp, vp, i32, i32, vp]),
+    "pn_mask_tc_workspace_bytes": (sz, [i32, i32]),
+    "pn_attn_mask_bits_tc": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
+    "pn_mask_pred_tc": (i32, [vp, vp, vp, i32, i32, i32, vp, sz, vp]),
     "pn_linear": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "pn_linear_tc_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_linear_tc": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),

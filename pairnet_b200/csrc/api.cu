@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -192,12 +192,55 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
   return 0;
 }
 
+// ---- mask einsums on the tcgen05 GEMM (rows 2 of SURVEY §8a).  Orientation: keys / pixels are the 128-row M tiles
+// (streamed raw, split hi/lo in the SM), the <= 256 queries of one image are the N extent (mask embeddings,
+// pre-split), so one accumulator column holds one query and one TMEM lane one key.
+//   bits : sign + ballot epilogue -> packed attention mask (one 32-bit word per warp and query)
+//   pred : transposed store -> mask_pred[b][q][pixel]
+static int maskbits_tc(const float* e, float* eh, float* el, const float* Ftok_l, uint32_t* bits, int* rowany, int B,
+                       int N, int hw, int words, cudaStream_t st) {
+  PN_REQUIRE(N <= 256, PN_ERR_UNSUPPORTED, "mask bits on tensor cores: at most 256 queries (got %d)", N);
+  PN_TRY(launch_split_tf32(e, eh, el, (size_t)B * N * D, st));
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    UmmaOperand o[4];
+    int nb = 0;
+    for (int bi = b0; bi < B && nb < 4; ++bi, ++nb) {
+      o[nb] = UmmaOperand{Ftok_l + (size_t)bi * hw * D, nullptr, D, eh + (size_t)bi * N * D, el + (size_t)bi * N * D, D,
+                          nullptr, nullptr, 0, hw, N, D};
+      o[nb].a_is_raw = 1;
+      o[nb].bits = bits + (size_t)bi * N * words;
+      o[nb].rowany = rowany + (size_t)bi * N;
+      o[nb].bits_words = words;
+    }
+    PN_TRY(launch_umma_gemm(o, nb, 3, st));
+  }
+  return 0;
+}
+static int mask_pred_tc(const float* e, float* eh, float* el, const float* Ftok, float* mask_pred, int B, int N, int HW,
+                        cudaStream_t st) {
+  PN_TRY(launch_split_tf32(e, eh, el, (size_t)B * N * D, st));
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    UmmaOperand o[4];
+    int nb = 0;
+    for (int bi = b0; bi < B && nb < 4; ++bi, ++nb) {
+      o[nb] = UmmaOperand{Ftok + (size_t)bi * HW * D, nullptr, D, eh + (size_t)bi * N * D, el + (size_t)bi * N * D, D,
+                          nullptr, mask_pred + (size_t)bi * N * HW, HW, HW, N, D};
+      o[nb].a_is_raw = 1;
+      o[nb].t_rows = HW;
+    }
+    PN_TRY(launch_umma_gemm(o, nb, 3, st));
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 struct M2FPlan {
   int B, N, M, L, nl, ffn;
   int hw[PN_MAX_LEVELS], ldf[PN_MAX_LEVELS];
   int maxhw, maxldf;
   size_t mha_bytes;
+  bool tc_mask;    // mask einsums (attention-mask bits, final mask_pred) on the tcgen05 GEMM, token-major operands
+  bool need_ftok;  // ... and mask_features arrives NCHW: a token-major copy is made first
 };
 
 static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
@@ -207,6 +250,10 @@ static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
   PN_REQUIRE(p.L >= 1 && p.L <= PN_MAX_LEVELS, PN_ERR_BAD_ARG, "m2f: num_levels out of range");
   PN_REQUIRE(p.nl >= 1 && p.nl <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "m2f: num_layers out of range");
   PN_REQUIRE(in->H4 > 0 && in->W4 > 0 && in->mask_features, PN_ERR_BAD_ARG, "m2f: bad mask_features");
+  p.tc_mask = get_option(OPT_TENSOR_CORES) && get_option(OPT_MASK_TC);
+  p.need_ftok = p.tc_mask && !in->mask_features_token_major;
+  PN_REQUIRE(p.tc_mask || !in->mask_features_token_major, PN_ERR_UNSUPPORTED,
+             "m2f: token-major mask_features need the tensor-core mask path (PN_OPT_TENSOR_CORES / PN_OPT_MASK_TC)");
   p.maxhw = 0; p.maxldf = 0; p.mha_bytes = mha_workspace_bytes(p.B, p.N, p.N);
   for (int l = 0; l < p.L; ++l) {
     PN_REQUIRE(in->h[l] > 0 && in->w[l] > 0 && in->memory[l], PN_ERR_BAD_ARG, "m2f: bad level %d", l);
@@ -222,6 +269,7 @@ static int m2f_plan(const PnM2FWeights* w, const PnM2FInputs* in, M2FPlan& p) {
   return 0;
 }
 
+static size_t in_hw4(const PnM2FInputs* in, const M2FPlan&) { return (size_t)in->H4 * in->W4; }
 constexpr int TC_MIN_ROWS = 1024;  // memory levels with fewer tokens stay on the FFMA GEMM
 constexpr size_t PPN_L2_CHUNK_BYTES = 48u << 20;  // pair matrices of one PPN chunk (L2 is 126 MB)
 struct M2FBuffers {
@@ -233,10 +281,13 @@ struct M2FBuffers {
   float *K, *V;
   uint32_t* bits; int* rowany;
   float *x, *xpos, *xn, *e1, *e2, *e;
+  float *eh, *el;   // mask embeddings split hi/lo (B operand of the tensor-core mask GEMMs)
+  float *teh, *tel; // same for the (possibly deferred) output head
+  float* Ftok;      // token-major copy of NCHW mask_features (tc_mask only)
   LayerScratch ls;
 };
 
-static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2FBuffers& b) {
+static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2FBuffers& b, bool own_tail = true) {
   for (int l = 0; l < p.L; ++l) {
     b.X[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
     b.XP[l] = ws.take<float>((size_t)p.B * p.hw[l] * D);
@@ -263,6 +314,13 @@ static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2F
   b.e1 = ws.take<float>((size_t)p.M * D);
   b.e2 = ws.take<float>((size_t)p.M * D);
   b.e = ws.take<float>((size_t)p.M * D);
+  b.eh = ws.take<float>((size_t)p.M * D);
+  b.el = ws.take<float>((size_t)p.M * D);
+  if (own_tail) {  // otherwise the caller provides buffers that outlive this stage (deferred output head)
+    b.teh = ws.take<float>((size_t)p.M * D);
+    b.tel = ws.take<float>((size_t)p.M * D);
+    b.Ftok = p.need_ftok ? ws.take<float>((size_t)p.B * in_hw4(in, p) * D) : nullptr;
+  }
   layer_scratch_take(ws, b.ls, p.M, p.ffn, p.mha_bytes);
 }
 
@@ -270,6 +328,8 @@ static void m2f_take(Workspace& ws, const M2FPlan& p, const PnM2FInputs* in, M2F
 // outlive this stage's scratch; the caller joins on `done` before reading them.
 struct TailCtx {
   float *xn, *e1, *e2, *e;   // [M,256] each, caller-owned
+  float *eh, *el;            // [M,256] split mask embeddings (tensor-core mask_pred)
+  float* ftok;               // [B,HW4,256] token-major mask_features copy, or null when the input already is
   cudaEvent_t done;
   bool deferred;
 };
@@ -280,13 +340,26 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
   PN_TRY(m2f_plan(w, in, p));
   PN_REQUIRE(out && out->cls_pred && out->mask_pred, PN_ERR_BAD_ARG, "m2f: null outputs");
   M2FBuffers b{};
-  m2f_take(ws, p, in, b);
+  m2f_take(ws, p, in, b, tail == nullptr);
   PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "m2f: workspace too small (%zu needed so far, %zu given)", ws.off,
              ws.cap);
   const int HW4 = in->H4 * in->W4;
   Side* sd = get_option(OPT_OVERLAP) ? get_side() : nullptr;
   cudaStream_t s2 = sd ? sd->s2 : st;
-  if (tail) { b.xn = tail->xn; b.e1 = tail->e1; b.e2 = tail->e2; b.e = tail->e; tail->deferred = false; }
+  if (tail) {
+    b.xn = tail->xn; b.e1 = tail->e1; b.e2 = tail->e2; b.e = tail->e; tail->deferred = false;
+    b.teh = tail->eh; b.tel = tail->el; b.Ftok = tail->ftok;
+  }
+  const bool tcm = p.tc_mask;
+  const float* Ftok = nullptr;  // mask_features as [B,HW4,256]
+  if (tcm) {
+    Ftok = in->mask_features;
+    if (p.need_ftok) {
+      PN_REQUIRE(b.Ftok, PN_ERR_WORKSPACE, "m2f: no buffer for the token-major mask_features copy");
+      PN_TRY(launch_nchw_to_tokens(in->mask_features, b.Ftok, p.B, HW4, st));
+      Ftok = b.Ftok;
+    }
+  }
 
   // ---- row 1 + the linear half of row 2 that does not depend on the queries
   for (int l = 0; l < p.L; ++l) {
@@ -308,8 +381,11 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     else
       PN_TRY(launch_level_prep(in->memory[l], w->level_embed + (size_t)l * D, pos, b.X[l], b.XP[l], p.B, p.hw[l], st,
                                x_split ? b.Xlo[l] : nullptr, xp_split ? b.XPlo[l] : nullptr));
-    PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
-                                      st));
+    if (tcm)
+      PN_TRY(launch_mask_feature_resize_tokens(Ftok, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], st));
+    else
+      PN_TRY(launch_mask_feature_resize(in->mask_features, b.Fl[l], p.B, in->H4, in->W4, in->h[l], in->w[l], p.ldf[l],
+                                        st));
   }
   if (sd) PN_TRY(side_wait(s2, side_record(sd, st)));  // fork: the side stream sees the prepared memories
   cudaEvent_t kv_free[PN_MAX_LAYERS];
@@ -386,7 +462,10 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     // ---- query side: forward_head (mask branch only): attn_mask = (mask_embed(post_norm(x)) . resize(F) < 0)
     PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, st));
     PN_TRY(memset_async(b.rowany, 0, sizeof(int) * p.M, st));
-    PN_TRY(launch_gemm_nmajor_maskbits(b.e, b.Fl[l], b.bits, b.rowany, p.B, p.N, p.hw[l], p.ldf[l], st));
+    if (tcm)
+      PN_TRY(maskbits_tc(b.e, b.eh, b.el, b.Fl[l], b.bits, b.rowany, p.B, p.N, p.hw[l], words, st));
+    else
+      PN_TRY(launch_gemm_nmajor_maskbits(b.e, b.Fl[l], b.bits, b.rowany, p.B, p.N, p.hw[l], p.ldf[l], st));
     if (out->mask_trace) {
       PN_REQUIRE(out->trace_words >= words, PN_ERR_BAD_ARG, "m2f: trace_words too small");
       ++g_launches;
@@ -408,7 +487,9 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
   if (defer) PN_TRY(side_wait(s2, side_record(sd, st)));
   PN_TRY(linear1(b.xn, D, w->cls_embed, out->cls_pred, w->num_cls, p.M, w->num_cls, D, 0, ts));
   PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, ts));
-  {
+  if (tcm) {
+    PN_TRY(mask_pred_tc(b.e, b.teh, b.tel, Ftok, out->mask_pred, p.B, p.N, HW4, ts));
+  } else {
     GemmProb g = make_linear(b.e, D, in->mask_features, nullptr, out->mask_pred, HW4, p.N, HW4, D);
     g.ldw = HW4;
     g.nb = p.B; g.sA = (long long)p.N * D; g.sW = (long long)D * HW4; g.sC = (long long)p.N * HW4;
@@ -610,6 +691,34 @@ int pn_attn_mask_bits(const float* E, const float* F, uint32_t* bits, int* rowan
   return launch_gemm_nmajor_maskbits(E, F, bits, rowany, B, N, hw, ldf, as_stream(stream));
 }
 
+int pn_mask_feature_resize_tokens(const float* mask_feature, float* out, int B, int H, int W, int h, int w,
+                                  pn_stream_t stream) {
+  return launch_mask_feature_resize_tokens(mask_feature, out, B, H, W, h, w, as_stream(stream));
+}
+int pn_nchw_to_tokens(const float* src, float* dst, int B, int HW, pn_stream_t stream) {
+  return launch_nchw_to_tokens(src, dst, B, HW, as_stream(stream));
+}
+size_t pn_mask_tc_workspace_bytes(int B, int N) { return 2 * (((size_t)B * N * D * sizeof(float) + 255) & ~size_t(255)) + 256; }
+int pn_attn_mask_bits_tc(const float* E, const float* F_tokens, uint32_t* bits, int* rowany, int B, int N, int hw,
+                         int words, void* wsp, size_t ws_bytes, pn_stream_t stream) {
+  PN_REQUIRE(E && F_tokens && bits && rowany && wsp, PN_ERR_BAD_ARG, "attn_mask_bits_tc: null pointer");
+  PN_REQUIRE(words * 32 >= hw && hw > 0, PN_ERR_BAD_ARG, "attn_mask_bits_tc: words*32 must cover hw");
+  Workspace ws(wsp, ws_bytes);
+  float* eh = ws.take<float>((size_t)B * N * D);
+  float* el = ws.take<float>((size_t)B * N * D);
+  PN_REQUIRE(ws.ok() && eh && el, PN_ERR_WORKSPACE, "attn_mask_bits_tc: workspace too small");
+  return maskbits_tc(E, eh, el, F_tokens, bits, rowany, B, N, hw, words, as_stream(stream));
+}
+int pn_mask_pred_tc(const float* E, const float* F_tokens, float* mask_pred, int B, int N, int HW, void* wsp,
+                    size_t ws_bytes, pn_stream_t stream) {
+  PN_REQUIRE(E && F_tokens && mask_pred && wsp && B > 0 && N > 0 && HW > 0, PN_ERR_BAD_ARG, "mask_pred_tc: bad args");
+  Workspace ws(wsp, ws_bytes);
+  float* eh = ws.take<float>((size_t)B * N * D);
+  float* el = ws.take<float>((size_t)B * N * D);
+  PN_REQUIRE(ws.ok() && eh && el, PN_ERR_WORKSPACE, "mask_pred_tc: workspace too small");
+  return mask_pred_tc(E, eh, el, F_tokens, mask_pred, B, N, HW, as_stream(stream));
+}
+
 int pn_mask_pred(const float* E, const float* F, float* mask_pred, int B, int N, int HW, pn_stream_t stream) {
   PN_REQUIRE(E && F && mask_pred && B > 0 && N > 0 && HW > 0, PN_ERR_BAD_ARG, "mask_pred: bad args");
   GemmProb g = make_linear(E, D, F, nullptr, mask_pred, HW, N, HW, D);
@@ -721,7 +830,9 @@ size_t pn_m2f_decoder_workspace_bytes(const PnM2FWeights* w, const PnM2FInputs* 
   if (m2f_plan(w, in, p) != 0) return 0;
   Workspace ws(nullptr, 0);
   M2FBuffers b{};
-  m2f_take(ws, p, nullptr, b);
+  PnM2FInputs nopos = *in;  // size for the worst case: position tables computed into the workspace
+  for (int l = 0; l < PN_MAX_LEVELS; ++l) nopos.pos[l] = nullptr;
+  m2f_take(ws, p, &nopos, b);
   return ws.off + 1024;
 }
 
@@ -787,7 +898,9 @@ size_t pn_head_workspace_bytes(const PnHeadWeights* w, const PnM2FInputs* in) {
   // stage scratch is reused (max), persistent taps are extra
   size_t stage = a > b ? a : b;
   stage = stage > c ? stage : c;
-  const size_t persist = ((size_t)B * N * D * 4 + 255) * 5 + ((size_t)B * 2 * R * D * 4 + 255) + 1024;
+  const bool need_ftok = get_option(OPT_TENSOR_CORES) && get_option(OPT_MASK_TC) && !in->mask_features_token_major;
+  const size_t persist = ((size_t)B * N * D * 4 + 255) * 7 + ((size_t)B * 2 * R * D * 4 + 255) + 1024 +
+                         (need_ftok ? ((size_t)B * in->H4 * in->W4 * D * 4 + 255) : 0);  // token-major mask_features copy
   return stage + persist;
 }
 
@@ -811,6 +924,10 @@ int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const PnHeadO
   tail.e1 = P.take<float>((size_t)B * N * D);
   tail.e2 = P.take<float>((size_t)B * N * D);
   tail.e = P.take<float>((size_t)B * N * D);
+  tail.eh = P.take<float>((size_t)B * N * D);
+  tail.el = P.take<float>((size_t)B * N * D);
+  const bool need_ftok = get_option(OPT_TENSOR_CORES) && get_option(OPT_MASK_TC) && !in->mask_features_token_major;
+  tail.ftok = need_ftok ? P.take<float>((size_t)B * HW4 * D) : nullptr;
   char* stage = (char*)ws + P.off;
   const size_t stage_bytes = ws_bytes - P.off;
 

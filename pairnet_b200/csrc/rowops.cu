@@ -327,6 +327,71 @@ int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, 
   return check_launch("mask_feature_resize_kernel");
 }
 
+// token-major variant: F [B,H*W,256] (channels_last mask_features) -> out [B,h*w,256]; same arithmetic
+__global__ void __launch_bounds__(256) mask_feature_resize_tokens_kernel(const float* __restrict__ F,
+                                                                          float* __restrict__ out, int H, int W, int h,
+                                                                          int w, float sh, float sw, long long n4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // float4 index over [B,h*w,64]
+  if (i >= n4) return;
+  const int cq = (int)(i & 63);
+  const long long tok = i >> 6;
+  const int hw = h * w;
+  const int b = (int)(tok / hw), o = (int)(tok - (long long)b * hw);
+  const int oy = o / w, ox = o - oy * w;
+  float sy = sh * ((float)oy + 0.5f) - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  float sx = sw * ((float)ox + 0.5f) - 0.5f;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int yp = (y0 < H - 1) ? 1 : 0, xq = (x0 < W - 1) ? 1 : 0;
+  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+  const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+  const float4* src = reinterpret_cast<const float4*>(F + (size_t)b * H * W * D) + cq;
+  const float4 v00 = __ldg(src + (size_t)(y0 * W + x0) * 64), v01 = __ldg(src + (size_t)(y0 * W + x0 + xq) * 64);
+  const float4 v10 = __ldg(src + (size_t)((y0 + yp) * W + x0) * 64);
+  const float4 v11 = __ldg(src + (size_t)((y0 + yp) * W + x0 + xq) * 64);
+  float4 r;
+  r.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+  r.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+  r.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+  r.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  reinterpret_cast<float4*>(out)[i] = r;
+}
+int launch_mask_feature_resize_tokens(const float* F, float* out, int B, int H, int W, int h, int w, cudaStream_t st) {
+  PN_REQUIRE(F && out && B > 0 && H > 0 && W > 0 && h > 0 && w > 0, PN_ERR_BAD_ARG, "mask_feature_resize_tokens: bad args");
+  PN_REQUIRE((((uintptr_t)F | (uintptr_t)out) & 15) == 0, PN_ERR_UNSUPPORTED, "mask_feature_resize_tokens: alignment");
+  const long long n4 = (long long)B * h * w * (D / 4);
+  mask_feature_resize_tokens_kernel<<<cdiv(n4, 256), 256, 0, st>>>(F, out, H, W, h, w, (float)H / (float)h,
+                                                                   (float)W / (float)w, n4);
+  return check_launch("mask_feature_resize_tokens_kernel");
+}
+
+// [B,256,HW] (NCHW) -> [B,HW,256] (token-major); 32x32 smem transpose tiles
+__global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + (size_t)b * D * HW;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + r * 8, p = p0 + tx;
+    tile[ty + r * 8][tx] = (p < HW) ? __ldg(s + (size_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + r * 8, c = c0 + tx;
+    if (p < HW) dst[((size_t)b * HW + p) * D + c] = tile[tx][ty + r * 8];
+  }
+}
+int launch_nchw_to_tokens(const float* src, float* dst, int B, int HW, cudaStream_t st) {
+  PN_REQUIRE(src && dst && B > 0 && HW > 0, PN_ERR_BAD_ARG, "nchw_to_tokens: bad args");
+  dim3 grid(cdiv(HW, 32), D / 32, B);
+  nchw_to_tokens_kernel<<<grid, 256, 0, st>>>(src, dst, HW);
+  return check_launch("nchw_to_tokens_kernel");
+}
+
 // dst[b,r,:] = src[b, idx[b,r], :]  (row length L floats); grid.x = B*R rows, grid.y = chunks
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src,
                                                            const int64_t* __restrict__ idx,

@@ -42,6 +42,11 @@ struct Problem {
   int relu;
   int t_rows;   // > 0: transposed store  C[(m / t_rows) * N + n][m % t_rows]  (row pitch ldc), e.g. V^T per image
   int bias_per_row;  // bias indexed by the output row m instead of the column n (weights as the A operand)
+  // sign/bit-pack epilogue (boolean attention mask, pairnet_head.py:244-256): rows = keys, columns = queries;
+  // bits[q * bits_words + m / 32] bit (m % 32) = (acc[m][q] < 0) | (m >= M); rowany[q] |= 1 if any key is open
+  uint32_t* bits;
+  int* rowany;
+  int bits_words;
 };
 constexpr int MAX_PROBLEMS = 4;
 struct Params {
@@ -253,21 +258,44 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
         }
-        if (row < P.M && n0 + c0 < P.N && P.t_rows > 0) {
+        if (P.bits) {
+          if (n0 + c0 >= P.N) continue;
+          // one ballot per query column: the 32 lanes of this warp are 32 consecutive keys = one mask word
+          const bool key_ok = row < P.M;
+          uint32_t myword = 0xffffffffu;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t wd = __ballot_sync(0xffffffffu, !key_ok || __uint_as_float(v[j]) < 0.f);
+            if (lane == j) myword = wd;
+          }
+          const int q = n0 + c0 + lane;
+          const int wi = (tc.m0 >> 5) + quad;
+          if (q < P.N && wi < P.bits_words) {
+            P.bits[(size_t)q * P.bits_words + wi] = myword;
+            if (myword != 0xffffffffu) atomicOr(&P.rowany[q], 1);
+          }
+        } else if (row < P.M && n0 + c0 < P.N && P.t_rows > 0) {
           // transposed store: lanes hold consecutive rows -> each column is one coalesced 128-byte store
           const int bi = row / P.t_rows, r = row - bi * P.t_rows;
           const float* bias_c = bias_t + c0;
-          if (!P.C_lo && !P.relu && !P.bias_per_row && n0 + c0 + 32 <= P.N) {
-            // fast path (full chunk, plain store): one FADD + one STG per element, pointer bumped by the row pitch
+          if (!P.C_lo && !P.relu && !P.bias_per_row) {
+            // fast path (plain store): one FADD + one STG per element, pointer bumped by the row pitch
             float* dst = P.C + ((size_t)bi * P.N + n0 + c0) * P.ldc + r;
             const size_t pitch = (size_t)P.ldc;
+            const int nvalid = P.N - (n0 + c0);  // >= 1
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 bb = *reinterpret_cast<const float4*>(bias_c + j);
-              dst[0] = __uint_as_float(v[j]) + bb.x;
-              dst[pitch] = __uint_as_float(v[j + 1]) + bb.y;
-              dst[2 * pitch] = __uint_as_float(v[j + 2]) + bb.z;
-              dst[3 * pitch] = __uint_as_float(v[j + 3]) + bb.w;
+              if (j + 3 < nvalid) {
+                dst[0] = __uint_as_float(v[j]) + bb.x;
+                dst[pitch] = __uint_as_float(v[j + 1]) + bb.y;
+                dst[2 * pitch] = __uint_as_float(v[j + 2]) + bb.z;
+                dst[3 * pitch] = __uint_as_float(v[j + 3]) + bb.w;
+              } else {
+                if (j < nvalid) dst[0] = __uint_as_float(v[j]) + bb.x;
+                if (j + 1 < nvalid) dst[pitch] = __uint_as_float(v[j + 1]) + bb.y;
+                if (j + 2 < nvalid) dst[2 * pitch] = __uint_as_float(v[j + 2]) + bb.z;
+              }
               dst += 4 * pitch;
             }
             continue;
@@ -483,13 +511,13 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   int maxM = 0, maxN = 0;
   for (int i = 0; i < count; ++i) {
     const UmmaOperand& o = ops[i];
-    PN_REQUIRE(o.a_hi && o.w_hi && o.C && (passes == 1 || ((o.a_lo || o.a_is_raw) && o.w_lo)), PN_ERR_BAD_ARG,
+    PN_REQUIRE(o.a_hi && o.w_hi && (o.C || o.bits) && (passes == 1 || ((o.a_lo || o.a_is_raw) && o.w_lo)), PN_ERR_BAD_ARG,
                "umma: null operand");
     PN_REQUIRE(!o.a_is_raw || passes == 3, PN_ERR_BAD_ARG, "umma: raw A operands need passes == 3");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
     PN_REQUIRE(o.bias_per_row || cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N,
                BIAS_MAX);
-    PN_REQUIRE(o.t_rows > 0 || (o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0), PN_ERR_UNSUPPORTED,
+    PN_REQUIRE(o.bits || o.t_rows > 0 || (o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0), PN_ERR_UNSUPPORTED,
                "umma: C must be 16B aligned");
     Problem& p = prm.p[i];
     PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
@@ -498,6 +526,8 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
     p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
+    p.bits = o.bits; p.rowany = o.rowany; p.bits_words = o.bits_words;
+    PN_REQUIRE(!o.bits || (o.rowany && o.bits_words > 0), PN_ERR_BAD_ARG, "umma: bit-pack epilogue needs rowany/words");
     PN_REQUIRE(!o.bias_per_row || o.M <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: per-row bias needs M <= %d", BIAS_MAX);
     PN_REQUIRE(!o.C_lo || ((uintptr_t)o.C_lo & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C_lo must be 16B aligned");
     maxM = o.M > maxM ? o.M : maxM;

@@ -243,15 +243,22 @@ class CrossHead2(nn.Module):
         if dev.type != "cuda":
             raise nat.NativeError("CrossHead2.forward needs CUDA tensors on a B200; there is no CPU fallback")
         stream = torch.cuda.current_stream(dev).cuda_stream
-        mask_features = mask_features.float().contiguous()
+        mask_features = mask_features.float()
         memorys = [m.float() for m in memorys]
         B, Cc, H4, W4 = mask_features.shape
+        # a channels_last mask_features map is consumed in place as token-major [B,H4*W4,256] by the tensor-core mask path
+        mf_tokens = (not mask_features.is_contiguous() and mask_features.stride() == (H4 * W4 * Cc, 1, W4 * Cc, Cc)
+                     and mask_features.data_ptr() % 16 == 0 and lib.pn_get_option(nat.PN_OPT_TENSOR_CORES) != 0
+                     and lib.pn_get_option(nat.PN_OPT_MASK_TC) != 0)
+        if not mf_tokens:
+            mask_features = mask_features.contiguous()
         assert Cc == nat.EMBED_DIMS and len(memorys) == self.num_transformer_feat_level
         N, R, K = self.num_queries, self.num_rel_query, self.num_rel_query
         ncls, nrel = self.num_classes + 1, self.num_relations
         w = self.native_weights()
         inp = nat.PnM2FInputs()
         inp.B, inp.H4, inp.W4, inp.mask_features = B, H4, W4, mask_features.data_ptr()
+        inp.mask_features_token_major = int(mf_tokens)
         keep = []
         for l, m in enumerate(memorys):
             # the pixel decoder hands out NCHW *views* of its token-major encoder output ([B,nq,256] sliced per

@@ -337,6 +337,19 @@ class MSDeformAttnPixelDecoder(nn.Module):
             return None
         lib = nat.load()
         cout = conv.out_channels
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        if (cout == nat.EMBED_DIMS and lib.pn_get_option(nat.PN_OPT_TENSOR_CORES) != 0
+                and lib.pn_get_option(nat.PN_OPT_MASK_TC) != 0):
+            # the head's tensor-core mask path consumes mask_features token-major: keep the map channels_last
+            # (same values, logical NCHW shape) -- plain [B*HW,256] x [256,256]^T GEMM, activations split in the SM
+            wsp = self._scratch("_mf_ws", 2 * cout * Cc * 4, x.device)
+            wh, wl = wsp.data_ptr(), wsp.data_ptr() + cout * Cc * 4
+            nat.check(lib.pn_split_tf32(conv.weight.data_ptr(), wh, wl, cout * Cc, stream), "pn_split_tf32")
+            y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device,
+                            memory_format=torch.channels_last)
+            nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), wh, wl, conv.bias.data_ptr() if conv.bias is not None else None,
+                                            y.data_ptr(), cout, B * H * W, cout, Cc, stream), "pn_linear_tc_rawa")
+            return y
         ws = self._scratch("_mf_ws", lib.pn_conv1x1_nhwc_to_nchw_workspace_bytes(cout), x.device)
         y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
         nat.check(lib.pn_conv1x1_nhwc_to_nchw(x.data_ptr(), conv.weight.data_ptr(),

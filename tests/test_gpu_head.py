@@ -277,6 +277,30 @@ def test_overlap_and_tensor_core_options_are_result_neutral(heads):
         lib.pn_set_option(0, 1)
 
 
+def test_channels_last_mask_features_and_mask_tc_option(heads):
+    """mask_features handed over channels_last (token-major, what the native pixel decoder produces) gives the same
+    bits as the NCHW input (which the library first copies to token-major); the FFMA mask kernels
+    (PN_OPT_MASK_TC = 0) agree to fp32 noise."""
+    from oracle.make_golden import small_head_inputs
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    _, p = heads
+    mf, mems = small_head_inputs(2, (32, 48), 93)
+    mems_c = [m.cuda() for m in mems]
+    cls_a, msk_a = p.forward_from_memories(mf.cuda(), mems_c)
+    a = {k: v.clone() for k, v in {**cls_a, **msk_a}.items()}
+    cls_b, msk_b = p.forward_from_memories(mf.cuda().contiguous(memory_format=torch.channels_last), mems_c)
+    for k, v in {**cls_b, **msk_b}.items():
+        assert torch.equal(a[k], v), k
+    try:
+        lib.pn_set_option(nat.PN_OPT_MASK_TC, 0)
+        cls_c, msk_c = p.forward_from_memories(mf.cuda().contiguous(memory_format=torch.channels_last), mems_c)
+        assert rel_err(cls_c["cls"], a["cls"]) < 1e-4
+        assert rel_err(msk_c["mask"], a["mask"]) < 1e-4
+    finally:
+        lib.pn_set_option(nat.PN_OPT_MASK_TC, 1)
+
+
 def _ref_cases():
     from oracle.pin_reference import REF_CASES
     return REF_CASES

@@ -174,6 +174,72 @@ def test_attn_mask_bits(hw):
     assert full[:, :, hw:].all()  # padding keys are blocked
 
 
+@pytest.mark.parametrize("hw,N,B", [(24, 100, 2), (1050, 100, 2), (4200, 100, 2), (700, 200, 1), (333, 37, 5)])
+def test_attn_mask_bits_tc(hw, N, B):
+    """tensor-core mask bits (tcgen05 3xTF32 GEMM, keys as M tiles, sign + warp-ballot epilogue) on token-major
+    features: same contract as the FFMA kernel."""
+    from pairnet_b200 import _native as nat, ops
+    lib = nat.load()
+    E = _t((B, N, 256), 19)
+    Ft = _t((B, hw, 256), 20)                       # token-major resized mask features
+    E[0, 4] = 0.0
+    Ft[B - 1] = Ft[B - 1].abs()
+    E[B - 1, 9] = -E[B - 1, 9].abs()
+    words = (hw + 63) // 64 * 2
+    Ec, Fc = E.cuda(), Ft.cuda()
+    bits = torch.zeros((B, N, words), dtype=torch.int32, device="cuda")
+    rowany = torch.zeros((B * N,), dtype=torch.int32, device="cuda")
+    need = lib.pn_mask_tc_workspace_bytes(B, N)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    nat.check(lib.pn_attn_mask_bits_tc(Ec.data_ptr(), Fc.data_ptr(), bits.data_ptr(), rowany.data_ptr(), B, N, hw, words,
+                                       ws.data_ptr(), need, torch.cuda.current_stream().cuda_stream), "bits_tc")
+    got = ops.unpack_bits(bits, hw).cpu()
+    logits = torch.einsum("bqc,bpc->bqp", E.double(), Ft.double())
+    ref = logits < 0
+    sure = logits.abs() > 1e-4
+    assert torch.equal(got[sure], ref[sure])
+    assert (got != ref).float().mean() < 1e-5
+    assert not got[0, 4].any() and got[B - 1, 9].all()
+    ra = rowany.cpu().view(B, N)
+    assert ra[B - 1, 9] == 0 and ra[0, 4] == 1
+    assert torch.equal(ra.bool(), ~got.all(-1))
+    full = ops.unpack_bits(bits, words * 32).cpu()
+    assert full[:, :, hw:].all()  # padding keys are blocked
+
+
+@pytest.mark.parametrize("B,N,H,W", [(2, 100, 23, 31), (1, 200, 40, 56), (3, 37, 16, 24)])
+def test_mask_pred_tc_and_token_layout_helpers(B, N, H, W):
+    """final mask_pred on the tcgen05 GEMM with a transposed store; NCHW -> token-major copy is exact."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    st = torch.cuda.current_stream().cuda_stream
+    E, Fm = _t((B, N, 256), 21), _t((B, 256, H, W), 22)
+    Ec, Fc = E.cuda(), Fm.cuda()
+    Ft = torch.empty((B, H * W, 256), device="cuda")
+    nat.check(lib.pn_nchw_to_tokens(Fc.data_ptr(), Ft.data_ptr(), B, H * W, st), "nchw_to_tokens")
+    assert torch.equal(Ft.cpu(), Fm.flatten(2).transpose(1, 2))
+    need = lib.pn_mask_tc_workspace_bytes(B, N)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    out = torch.full((B, N, H, W), float("nan"), device="cuda")
+    nat.check(lib.pn_mask_pred_tc(Ec.data_ptr(), Ft.data_ptr(), out.data_ptr(), B, N, H * W, ws.data_ptr(), need, st),
+              "mask_pred_tc")
+    # 3xTF32 (hi/lo split operands on the tensor pipe): fp32-level, slightly above the FFMA kernel's 2e-6
+    assert rel_err(out.cpu(), torch.einsum("bqc,bchw->bqhw", E.double(), Fm.double())) < 5e-6
+
+
+@pytest.mark.parametrize("H,W,h,w", [(32, 48, 4, 6), (40, 56, 20, 28), (200, 334, 25, 42)])
+def test_mask_feature_resize_tokens(H, W, h, w):
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    Fm = _t((2, 256, H, W), 4)
+    ref = F.interpolate(Fm, (h, w), mode="bilinear", align_corners=False).flatten(2).transpose(1, 2)
+    Ft = Fm.cuda().contiguous(memory_format=torch.channels_last)
+    out = torch.empty((2, h * w, 256), device="cuda")
+    nat.check(lib.pn_mask_feature_resize_tokens(Ft.data_ptr(), out.data_ptr(), 2, H, W, h, w,
+                                                torch.cuda.current_stream().cuda_stream), "resize_tokens")
+    assert float((out.cpu() - ref).abs().max()) < 2e-6 * float(ref.abs().max()) + 1e-6
+
+
 def test_mask_pred():
     from pairnet_b200 import ops
     E, Fm = _t((2, 100, 256), 21), _t((2, 256, 23, 31), 22)
@@ -398,7 +464,8 @@ def test_pixel_decoder_native_tail_vs_torch():
         mf_n, mem_n = m(feats)
         m.tail_impl = "torch"
         mf_t, mem_t = m(feats)
-    assert mf_n.is_contiguous() and mf_n.shape == mf_t.shape
+    # token-major (channels_last) for the head's tensor-core mask path; NCHW-contiguous when that path is off
+    assert mf_n.is_contiguous(memory_format=torch.channels_last) and mf_n.shape == mf_t.shape
     for a, b in zip(mem_n, mem_t):
         assert torch.equal(a, b)
     assert rel_err(mf_n, mf_t) < 1e-3  # the 3x3 output conv (cuDNN, TF32) is shared; the 1x1 is fp32-accurate here
