@@ -154,6 +154,7 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
     LnArgs n{};
     n.x = s.proj; n.nparts = 1; n.resid = x; n.gamma = L.norm[0].gamma; n.beta = L.norm[0].beta;
     n.y = s.x1; n.pos = qpos; n.pos_mod = Nq; n.ypos = xpos; n.M = M;
+    n.zero_rows = const_cast<int*>(rowany);  // the attention above was the last reader: clear for the next layer's bits
     PN_TRY(launch_layernorm(n, st));
   }
   // ---- self attention: q = k = (x1 + qpos) W{q,k}^T, v = x1 Wv^T
@@ -394,6 +395,7 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
   {
     LnArgs n{};
     n.x = b.x; n.nparts = 1; n.gamma = w->post_norm.gamma; n.beta = w->post_norm.beta; n.y = b.xn; n.M = p.M;
+    n.zero_rows = b.rowany;  // every later clear rides on the cross-attention LayerNorm of the layer that consumed it
     PN_TRY(launch_layernorm(n, st));
   }
   for (int i = 0; i < p.nl; ++i) {
@@ -461,7 +463,6 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     cudaEvent_t kv_ready = sd ? side_record(sd, s2) : nullptr;
     // ---- query side: forward_head (mask branch only): attn_mask = (mask_embed(post_norm(x)) . resize(F) < 0)
     PN_TRY(mlp3(b.xn, w->mask_embed, b.e1, b.e2, b.e, p.M, st));
-    PN_TRY(memset_async(b.rowany, 0, sizeof(int) * p.M, st));
     if (tcm)
       PN_TRY(maskbits_tc(b.e, b.eh, b.el, b.Fl[l], b.bits, b.rowany, p.B, p.N, p.hw[l], words, st));
     else

@@ -126,6 +126,7 @@ struct LnArgs {
   const float* gamma2;     // optional chained second LN (post_norm)
   const float* beta2;
   float* y2;
+  int* zero_rows;          // optional [M] int32 cleared by this launch (attention-mask `rowany` flags, consumed upstream)
   int M;
 };
 int launch_layernorm(const LnArgs& a, cudaStream_t st);

@@ -278,7 +278,16 @@ int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) 
   const int qtiles = cdiv(a.Nq, TQ);
   const int base = a.B * NH * qtiles;
   const int total_tiles = cdiv(a.Nk, TKEYS);
-  int want = cdiv(148, base);
+  // one CTA per SM (TMEM: 512 columns; smem: 160 KB): keep the grid within ONE wave -- B*8*qtiles*splits <= #SMs --
+  // a second, nearly empty wave doubles the kernel time (measured: 160 CTAs 103 us -> 144 CTAs 56 us at hw = 16 700)
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  int want = num_sms / base;
   want = want < 1 ? 1 : (want > 64 ? 64 : want);
   want = want > total_tiles ? total_tiles : want;
   prm.tiles_per_split = cdiv(total_tiles, want);

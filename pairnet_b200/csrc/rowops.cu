@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= a.M) return;
+  if (a.zero_rows && lane == 0) a.zero_rows[m] = 0;
   float v[8];
   load_row(v, a.x + (size_t)m * D, lane);
   for (int s = 1; s < a.nparts; ++s) {  // fixed order -> deterministic split-K reduction
