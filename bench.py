@@ -5,8 +5,8 @@
 
 Workload (BASELINE.json configs[1]): Pair-Net R50 / Mask2Former, 100 object + 100 relation queries,
 bs = 2 per GPU, synthetic 800x1333 images, fp32.  One "step" = one forward of the whole detector
-(ResNet-50 + MSDeformAttn pixel decoder in PyTorch/cuDNN, then the hand-written CUDA head:
-masked-attention decoder -> Pair Proposal Network -> Relation Fusion).  Metric: images/sec.
+(ResNet-50 on cuDNN; MSDeformAttn pixel decoder = cuDNN convs + hand-written encoder / GroupNorm / FPN merge; then the
+hand-written CUDA head: masked-attention decoder -> Pair Proposal Network -> Relation Fusion).  Metric: images/sec.
 
 * value      : device-resident inputs, whole forward replayed as one CUDA graph, CUDA-event timed.
 * e2e        : the same through the public API (`PSGTr.forward_dummy`-equivalent) from PINNED HOST
@@ -256,8 +256,8 @@ def dominant_kernel_roofline(model, device, pk):
                                          "split in-SM through TMEM), K/V-projection problem of the 100x167 level, "
                                          "M=33400 N=512 K=256",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": 54.48e6, "traffic_source": "ncu --set full r01 capture (profiles/r01_umma_gemm_ncu.md): "
-                                                  "dram read 35.32 MB + write 19.16 MB per launch",
+            "traffic": 52.79e6, "traffic_source": "ncu --set full r01g capture (profiles/r01g_tcgen05_kernels_ncu.md): "
+                                                  "dram read 35.35 MB + write 17.43 MB per launch",
             "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": flops, "tensor_pipe_flops_per_launch": 3 * flops,
             "peak_source": pk["source"], "ffma_kernel_ms_same_problem": ms_ffma,
@@ -398,7 +398,8 @@ def run_b200(args, rank, world, local):
                    "image": [IMG_H, IMG_W], "queries": 100, "parallelism": f"dp{world} (replicas, no forward collective)",
                    "l2_flush": "256 MiB read+write between timed steps (outside the event pair)",
                    "cuda_graph": not args.no_graph,
-                   "upstream": "ResNet-50 + MSDeformAttn pixel decoder in PyTorch (cuDNN TF32 conv default, fp32 matmul)"},
+                   "upstream": "ResNet-50 and the pixel decoder's 1x1/3x3 convs on cuDNN (TF32 conv default, as PyTorch); "
+                               "deformable encoder, GroupNorm, FPN merge and mask_feature conv hand-written (3xTF32 / fp32)"},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
                 "result": "all_cls_scores (sub,obj,cls,rel,importance) + sub_pos/obj_pos to pinned host; mask tensors stay on device"},
