@@ -266,6 +266,19 @@ PN_API int pn_relation_fusion_forward(const PnRelWeights* w, const float* pair_f
 PN_API int pn_gather_rows(const float* src, const int64_t* idx, float* dst, int B, int Nsrc, int R,
                    long long L, pn_stream_t stream);
 
+/* ------------------------------------------------------------------ inference post-processing
+ * replaces the heavy part of CrossHead2._get_bboxes_single, pairnet_head.py:826-905: the three full-image
+ * F.interpolate(bilinear, align_corners=False) + sigmoid > 0.5 / softmax-argmax / per-mask area counts.  Both read the
+ * quarter-resolution logits [N,h,w] of ONE image and evaluate the interpolation on the fly.
+ *   pn_upsample_threshold: out[r] = (up(mask[idx[r]]) > 0) as uint8 [R,H,W]; idx NULL = rows 0..R-1 (then R <= N).
+ *   pn_panoptic_merge    : m = argmax_k up(mask[keep_idx[k]]) (first maximum), id = remap[m] (stuff de-duplication),
+ *                          pan[y][x] = id * instance_offset + labels[id] (int64), area[id] += 1 (area is zeroed here). */
+PN_API int pn_upsample_threshold(const float* mask, const int64_t* idx, uint8_t* out, int N, int R, int h, int w, int H,
+                                 int W, pn_stream_t stream);
+PN_API int pn_panoptic_merge(const float* mask, const int* keep_idx, const int* remap, const int64_t* labels, int n_keep,
+                             int h, int w, int H, int W, long long instance_offset, int64_t* pan, int* area,
+                             pn_stream_t stream);
+
 /* ------------------------------------------------------------------ upstream "next" row
  * The 6-layer multi-scale deformable-attention encoder of mmdet's MSDeformAttnPixelDecoder
  * (cfg configs/mask2former/pairnet.py:38-66; called from pairnet_head.py:262).  8 heads x 32. */

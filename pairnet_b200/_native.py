@@ -135,6 +135,8 @@ SIGNATURES = {
     "pn_relation_fusion_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "pn_relation_fusion_forward": (i32, [P(PnRelWeights), vp, vp, vp, i32, i32, vp, sz, vp]),
     "pn_gather_rows": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
+    "pn_upsample_threshold": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "pn_panoptic_merge": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_longlong, vp, vp, vp]),
     "pn_msda_encoder_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
     "pn_msda_encoder_forward": (i32, [P(PnMsdaEncoderWeights), vp, vp, P(i32), P(i32), vp, i32, vp, sz, vp]),
     "pn_group_norm_workspace_bytes": (sz, [i32, i32, i32]),

@@ -43,8 +43,11 @@ class PSGTr(nn.Module):
         raise NotImplementedError("training (psgtr.py:112-146) depends on SURVEY §8f rank 2 (targets + losses)")
 
     def simple_test(self, img, img_metas, rescale=False):
+        """psgtr.py:148-156: head post-processing -> one ``Result`` per image."""
+        from .results import triplet2Result
         feat = self.extract_feat(img)
-        return self.bbox_head.simple_test(feat, img_metas, rescale=rescale)
+        results_list = self.bbox_head.simple_test(feat, img_metas, rescale=rescale)
+        return [triplet2Result(triplets, self.bbox_head.use_mask) for triplets in results_list]
 
     def forward(self, img, img_metas=None, return_loss=False, **kwargs):
         if return_loss:

@@ -53,6 +53,9 @@ def _ptr(t):
     return t.data_ptr()
 
 
+INSTANCE_OFFSET = 1000  # mmdet.datasets.coco_panoptic.INSTANCE_OFFSET (pairnet_head.py:16)
+
+
 @HEADS.register_module()
 class CrossHead2(nn.Module):
     def __init__(self, num_classes, in_channels, num_relations, num_obj_query=100, num_rel_query=100,
@@ -147,10 +150,89 @@ class CrossHead2(nn.Module):
     def forward_train(self, *args, **kwargs):
         raise NotImplementedError("training targets/losses (pairnet_head.py:419-757) are SURVEY §8f rank 2, not built yet")
 
+    # ------------------------------------------------------------------ inference post-processing (pairnet_head.py:759-930)
     def simple_test_bboxes(self, feats, img_metas, rescale=False):
-        raise NotImplementedError("post-processing (pairnet_head.py:759-924) is SURVEY §8f rank 3, not built yet")
+        """pairnet_head.py:926-930."""
+        outs = self.forward(feats, img_metas)
+        return self.get_bboxes(*outs, img_metas, rescale=rescale)
 
     simple_test = simple_test_bboxes
+
+    def get_bboxes(self, cls_scores, mask_preds, img_metas, rescale=False):
+        """pairnet_head.py:759-786: per image -> (det_bboxes[2K,5], labels[2K], rel_pairs[K,2] int32, masks[2K,H,W] bool,
+        pan_img[H,W] long (CPU), r_scores[K], r_labels[K], r_dists[K,num_relations+1])."""
+        return [self._get_bboxes_single(mask_preds["mask"][i], cls_scores["cls"][i], cls_scores["sub"][i],
+                                        cls_scores["obj"][i], cls_scores["rel"][i], mask_preds["sub_seg"][i],
+                                        mask_preds["obj_seg"][i], img_metas[i]["img_shape"],
+                                        img_metas[i]["scale_factor"], rescale)
+                for i in range(len(img_metas))]
+
+    @torch.no_grad()
+    def _get_bboxes_single(self, all_masks, all_cls_score, s_cls_score, o_cls_score, r_cls_score, s_mask_pred,
+                           o_mask_pred, img_shape, scale_factor, rescale=False):
+        """pairnet_head.py:788-924.  The class / relation softmaxes are [K,134]-sized torch plumbing; the three
+        full-image upsamples, the thresholds, the panoptic argmax and the per-segment areas run in
+        ``pn_upsample_threshold`` / ``pn_panoptic_merge`` straight from the quarter-resolution logits."""
+        from torch.nn import functional as F
+        lib = nat.load()
+        dev = all_masks.device
+        if dev.type != "cuda":
+            raise nat.NativeError("CrossHead2.get_bboxes needs CUDA tensors on a B200; there is no CPU fallback")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        assert len(s_cls_score) == len(o_cls_score) == len(r_cls_score)
+        H, W = round(img_shape[0] / float(scale_factor[1])), round(img_shape[1] / float(scale_factor[0]))
+        s_logits = F.softmax(s_cls_score, dim=-1)[..., :-1]
+        o_logits = F.softmax(o_cls_score, dim=-1)[..., :-1]
+        s_labels, o_labels = s_logits.argmax(-1) + 1, o_logits.argmax(-1) + 1
+        r_dists = F.softmax(r_cls_score, dim=-1).reshape(-1, self.num_relations)
+        r_dists = torch.cat([torch.zeros(self.num_rel_query, 1, device=dev), r_dists], dim=-1)
+        complete_labels = torch.cat((s_labels, o_labels), 0)
+        all_scores, all_labels = F.softmax(all_cls_score, dim=-1)[..., :-1].max(-1)
+        all_masks = all_masks.float().contiguous()
+        N, h, w = all_masks.shape
+        K = s_cls_score.shape[0]
+        masks = torch.empty((2 * K, H, W), dtype=torch.bool, device=dev)
+        for half, src in enumerate((s_mask_pred, o_mask_pred)):
+            src = src.float().contiguous()
+            assert src.shape == (K, h, w)
+            nat.check(lib.pn_upsample_threshold(src.data_ptr(), None, masks[half * K:].data_ptr(), K, K, h, w, H, W,
+                                                stream), "pn_upsample_threshold")
+        keep = (all_labels != s_logits.shape[-1] - 1) & (all_scores > 0.5)
+        keep_idx = keep.nonzero().flatten().to(torch.int32)
+        labels_k = all_labels[keep].contiguous()
+        if keep_idx.numel() == 0:
+            pan_img = torch.ones((H, W)).to(torch.long)
+        else:
+            pan = torch.empty((H, W), dtype=torch.int64, device=dev)
+
+            def merge(keep_idx, labels_k, remap):
+                n = keep_idx.numel()
+                if n == 0:  # the reference indexes an empty label list here
+                    raise IndexError("every kept mask was filtered as small (reference: all_labels[m_id] on an empty list)")
+                remap_t = torch.tensor(remap, dtype=torch.int32, device=dev)
+                area = torch.empty(n, dtype=torch.int32, device=dev)
+                nat.check(lib.pn_panoptic_merge(all_masks.data_ptr(), keep_idx.data_ptr(), remap_t.data_ptr(),
+                                                labels_k.data_ptr(), n, h, w, H, W, INSTANCE_OFFSET, pan.data_ptr(),
+                                                area.data_ptr(), stream), "pn_panoptic_merge")
+                return area.tolist()  # one small D2H per pass (the reference does one .item() per mask)
+
+            # stuff classes (label >= 80) seen more than once are merged into their first instance (:858-861, :877-882)
+            first, remap = {}, []
+            for k, lab in enumerate(labels_k.tolist()):
+                remap.append(first.setdefault(lab, k) if lab >= 80 else k)
+            area = merge(keep_idx, labels_k, remap)
+            while True:  # drop segments of <= 4 pixels and re-run the argmax without them (:896-908)
+                small = torch.tensor([a <= 4 for a in area], dtype=torch.bool, device=dev)
+                if not bool(small.any()):
+                    break
+                keep_idx, labels_k = keep_idx[~small].contiguous(), labels_k[~small].contiguous()
+                area = merge(keep_idx, labels_k, list(range(keep_idx.numel())))
+            pan_img = pan.cpu()
+        det_bboxes = torch.zeros((self.num_rel_query * 2, 5), device=dev)
+        r_scores = torch.zeros(self.num_rel_query, device=dev)
+        r_labels = torch.zeros(self.num_rel_query, device=dev)
+        rel_pairs = torch.arange(len(det_bboxes), dtype=torch.int).reshape(2, -1).T
+        return det_bboxes, complete_labels, rel_pairs, masks, pan_img, r_scores, r_labels, r_dists
 
     # ------------------------------------------------------------------ native plumbing
     def _hot_params(self):
