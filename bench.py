@@ -288,6 +288,51 @@ def ppn_microbench(device, pk):
     return out
 
 
+def postproc_inputs(device, B=PER_GPU_BATCH, N=100, K=100, hw4=(IMG_H // 4, (IMG_W + 3) // 4), seed=7):
+    """Synthetic head outputs that exercise the post-processing (confident thing / stuff / background queries, smooth
+    mask logits): random-init weights alone keep no segment (no class score exceeds 0.5)."""
+    g = torch.Generator().manual_seed(seed)
+    cls = torch.randn(B, N, 134, generator=g)
+    for b in range(B):
+        q = torch.randperm(N, generator=g)[:33]
+        c = torch.randint(0, 134, (33,), generator=g)
+        cls[b, q, c] += 14.0
+    lo = torch.randn(B, N, hw4[0] // 8, hw4[1] // 8, generator=g) * 4
+    mask = torch.nn.functional.interpolate(lo, size=hw4, mode="bicubic", align_corners=False).contiguous()
+    sp, op = torch.randint(0, N, (B, K), generator=g), torch.randint(0, N, (B, K), generator=g)
+    gat = lambda t, idx: torch.stack([t[b, idx[b]] for b in range(B)])
+    cls_scores = dict(cls=cls, sub=gat(cls, sp), obj=gat(cls, op), rel=torch.randn(B, K, 56, generator=g))
+    mask_preds = dict(mask=mask, sub_seg=gat(mask, sp), obj_seg=gat(mask, op))
+    metas = [dict(img_shape=(IMG_H, IMG_W, 3), scale_factor=[1.0, 1.0, 1.0, 1.0]) for _ in range(B)]
+    return cls_scores, mask_preds, metas
+
+
+def postproc_bench(head, device, with_cpu):
+    """`CrossHead2.get_bboxes` (pairnet_head.py:759-924) at 800x1333, B200 vs the CPU oracle."""
+    cls_scores, mask_preds, metas = postproc_inputs(device)
+    cu = lambda d: {k: v.to(device) for k, v in d.items()}
+    c, m = cu(cls_scores), cu(mask_preds)
+    head.get_bboxes(c, m, metas)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        res = head.get_bboxes(c, m, metas)
+    torch.cuda.synchronize()
+    gpu_ms = 1e3 * (time.perf_counter() - t0) / (reps * len(metas))
+    out = {"what": "get_bboxes: 2 x 100 mask upsample+threshold to 800x1333, panoptic argmax/areas, labels, rel dists",
+           "gpu_ms_per_image": gpu_ms, "segments_kept": int((res[0][4] // 1000).unique().numel()),
+           "timing": "host wall clock incl. the per-pass area D2H (post-processing is host-driven in the reference too)"}
+    if with_cpu:
+        from oracle import postproc as opp
+        one = lambda d: {k: v[:1] for k, v in d.items()}
+        t0 = time.perf_counter()
+        opp.get_bboxes(one(cls_scores), one(mask_preds), metas[:1], 56, 100)
+        out["cpu_oracle_ms_per_image"] = 1e3 * (time.perf_counter() - t0)
+        out["cpu_cores"] = torch.get_num_threads()
+    return out
+
+
 def run_b200(args, rank, world, local):
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     device = torch.device("cuda", local)
@@ -379,6 +424,7 @@ def run_b200(args, rank, world, local):
         e2e_value = world * PER_GPU_BATCH * args.steps / (e2e_ms * 1e-3)
         clk = clocks.stop()
 
+        post = postproc_bench(head, device, with_cpu=(world == 1 and not args.no_cpu_baseline)) if rank == 0 else None
         roof = dominant_kernel_roofline(model, device, pk) if rank == 0 else None
         micro = ppn_microbench(device, pk) if (rank == 0 and not args.no_ppn_microbench) else None
 
@@ -413,6 +459,8 @@ def run_b200(args, rank, world, local):
     }
     if micro is not None:
         line["ppn_microbench"] = micro
+    if post is not None:
+        line["postproc"] = post
     print(json.dumps(line), flush=True)
 
 
