@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU oracle leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-ppn-microbench", action="store_true", help="skip BASELINE config 5 (PPN only, ~2 s)")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true",
+                    help="keep cuDNN's heuristic algorithm choice for the upstream convolutions (default: autotune per shape "
+                         "during warm-up, the reference's `cudnn_benchmark=True` knob of tools/test.py:164-166)")
     ap.add_argument("--profile", action="store_true",
                     help="warm up, then run ONE eager forward between cudaProfilerStart/Stop and exit "
                          "(for `ncu --profile-from-start off`)")
@@ -337,6 +340,7 @@ def run_b200(args, rank, world, local):
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     pk = peaks()
     from pairnet_b200.detector import GraphedForward
     model = build_model(device)
@@ -443,7 +447,7 @@ def run_b200(args, rank, world, local):
         "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": world * PER_GPU_BATCH,
                    "image": [IMG_H, IMG_W], "queries": 100, "parallelism": f"dp{world} (replicas, no forward collective)",
                    "l2_flush": "256 MiB read+write between timed steps (outside the event pair)",
-                   "cuda_graph": not args.no_graph,
+                   "cuda_graph": not args.no_graph, "cudnn_benchmark": not args.no_cudnn_benchmark,
                    "upstream": "ResNet-50 and the pixel decoder's 1x1/3x3 convs on cuDNN (TF32 conv default, as PyTorch); "
                                "deformable encoder, GroupNorm, FPN merge and mask_feature conv hand-written (3xTF32 / fp32)"},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
