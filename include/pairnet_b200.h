@@ -305,6 +305,8 @@ PN_API size_t pn_group_norm_workspace_bytes(int B, int HW, int groups);
 PN_API int pn_group_norm(const float* x, const float* gamma, const float* beta, float* y, int B, int HW,
                          int groups, int relu, int channels_last, float eps, void* ws, size_t ws_bytes,
                          pn_stream_t stream);
+/* ResNet stem MaxPool2d(3, stride 2, padding 1) on a channels_last map: x [B,H,W,C] -> y [B,(H-1)/2+1,(W-1)/2+1,C] */
+PN_API int pn_maxpool3x3s2_nhwc(const float* x, float* y, int B, int H, int W, int C, pn_stream_t stream);
 /* GroupNorm fused with the FPN top-down merge of MSDeformAttnPixelDecoder.forward:
  *   y = GN(x) + F.interpolate(top, size=(H,W), mode="bilinear", align_corners=False)
  * x, y channels_last [B,H*W,256] (y may alias x); top token-major: element (b, ty, tx, c) at

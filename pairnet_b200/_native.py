@@ -141,6 +141,7 @@ SIGNATURES = {
     "pn_msda_encoder_forward": (i32, [P(PnMsdaEncoderWeights), vp, vp, P(i32), P(i32), vp, i32, vp, sz, vp]),
     "pn_group_norm_workspace_bytes": (sz, [i32, i32, i32]),
     "pn_group_norm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, sz, vp]),
+    "pn_maxpool3x3s2_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "pn_gn_upsample_add": (i32, [vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, C.c_float, vp, sz, vp]),
     "pn_conv1x1_nhwc_to_nchw_workspace_bytes": (sz, [i32]),
     "pn_conv1x1_nhwc_to_nchw": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),

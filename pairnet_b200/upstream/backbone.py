@@ -75,6 +75,8 @@ class ResNet(nn.Module):
                     setattr(blk, b, nn.Identity())
                 if blk.downsample is not None:
                     blk.downsample = nn.Sequential(fuse_conv_bn_eval(blk.downsample[0], blk.downsample[1]))
+                    # bias of the fused (conv3 + projection shortcut) epilogue, see _forward_fused_epilogues
+                    blk.shortcut_bias = (blk.conv3.bias + blk.downsample[0].bias).detach()
             stages.append(layer)
         fused = nn.ModuleList([stem] + stages).to(memory_format=torch.channels_last)
         for p in fused.parameters():
@@ -95,15 +97,38 @@ class ResNet(nn.Module):
                                                 conv.groups)
         return conv(x)
 
+    def _maxpool(self, x):
+        """stem max-pool: ``pn_maxpool3x3s2_nhwc`` on channels_last maps (ATen's NHWC kernel is 4x off the HBM bound)."""
+        mp = self.maxpool
+        geom = (mp.kernel_size, mp.stride, mp.padding, mp.dilation, mp.ceil_mode)
+        B, C, H, W = x.shape
+        if (geom not in ((3, 2, 1, 1, False), ((3, 3), (2, 2), (1, 1), (1, 1), False)) or C % 4 or x.dtype != torch.float32
+                or not x.is_contiguous(memory_format=torch.channels_last) or x.data_ptr() % 16):
+            return mp(x)
+        from .. import _native as nat
+        y = torch.empty((B, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        nat.check(nat.load().pn_maxpool3x3s2_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, C,
+                                                  torch.cuda.current_stream(x.device).cuda_stream), "pn_maxpool3x3s2_nhwc")
+        return y
+
     def _forward_fused_epilogues(self, f, x):
-        x = self.maxpool(self._conv_act(x, f[0]))
+        x = self._maxpool(self._conv_act(x, f[0]))
         outs = []
         for i in range(4):
             for blk in f[i + 1]:
-                identity = x if blk.downsample is None else blk.downsample[0](x)
                 y = self._conv_act(x, blk.conv1)
                 y = self._conv_act(y, blk.conv2)
-                x = self._conv_act(y, blk.conv3, residual=identity)
+                if blk.downsample is None:
+                    x = self._conv_act(y, blk.conv3, residual=x)
+                else:
+                    # relu(conv3(y) + b3 + conv_ds(x) + b_ds): the projection shortcut runs bias-free and its (folded-BN)
+                    # bias rides on conv3's fused epilogue instead of a separate elementwise pass over the map
+                    ds = blk.downsample[0]
+                    identity = torch.nn.functional.conv2d(x, ds.weight, None, ds.stride, ds.padding, ds.dilation, ds.groups)
+                    c3 = blk.conv3
+                    x = torch.cudnn_convolution_add_relu(y, c3.weight, identity, 1.0, blk.shortcut_bias, c3.stride,
+                                                         c3.padding, c3.dilation, c3.groups)
             if i in self.out_indices:
                 outs.append(x)
         return tuple(outs)

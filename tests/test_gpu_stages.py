@@ -471,6 +471,42 @@ def test_pixel_decoder_native_tail_vs_torch():
     assert rel_err(mf_n, mf_t) < 1e-3  # the 3x3 output conv (cuDNN, TF32) is shared; the 1x1 is fp32-accurate here
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 50, 67), (1, 64, 400, 667), (1, 8, 5, 4)])
+def test_maxpool3x3s2_nhwc_bit_exact(B, C, H, W):
+    from pairnet_b200 import _native as nat
+    x = _t((B, C, H, W), 71).cuda().contiguous(memory_format=torch.channels_last)
+    ref = F.max_pool2d(x, 3, 2, 1)
+    y = torch.empty_like(ref, memory_format=torch.channels_last)
+    nat.check(nat.load().pn_maxpool3x3s2_nhwc(x.data_ptr(), y.data_ptr(), B, H, W, C,
+                                              torch.cuda.current_stream().cuda_stream), "maxpool")
+    assert torch.equal(y, ref)
+
+
+def test_backbone_fused_epilogue_path_matches_module_path():
+    """upstream plumbing: BN-folded channels_last ResNet-50 with cuDNN fused epilogues, the native stem max-pool and the
+    projection-shortcut bias folded into conv3's epilogue vs the plain module path (both TF32 convs on the GPU)."""
+    from pairnet_b200.upstream.backbone import ResNet
+    torch.manual_seed(3)
+    m = ResNet(depth=50, norm_eval=True).cuda().eval()
+    with torch.no_grad():
+        for mod in m.modules():  # non-trivial frozen-BN statistics
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.1)
+        x = torch.randn(2, 3, 128, 160, device="cuda")
+        fast = m(x)
+        type(m).fuse_epilogues = False
+        try:
+            slow = m(x)
+        finally:
+            type(m).fuse_epilogues = True
+    for a, b in zip(fast, slow):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < 5e-3  # TF32 convolutions with different algorithms / summation orders
+
+
 # --------------------------------------------------------------------------- PPN at scale (BASELINE config 5)
 @pytest.mark.parametrize("B,N", [(12, 100), (7, 200), (3, 400), (30, 37), (9, 128), (8, 130), (600, 100)])
 def test_pair_matrix_tcgen05_and_topk_batched(B, N):
