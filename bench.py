@@ -315,14 +315,20 @@ def postproc_bench(head, device, with_cpu):
     cls_scores, mask_preds, metas = postproc_inputs(device)
     cu = lambda d: {k: v.to(device) for k, v in d.items()}
     c, m = cu(cls_scores), cu(mask_preds)
-    head.get_bboxes(c, m, metas)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
+    res = None
+    for _ in range(3):  # warm-up: the 2 x 213 MB result buffers settle in the caching allocator
+        del res
         res = head.get_bboxes(c, m, metas)
     torch.cuda.synchronize()
-    gpu_ms = 1e3 * (time.perf_counter() - t0) / (reps * len(metas))
+    reps, t_acc = 5, 0.0
+    for _ in range(reps):
+        del res
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = head.get_bboxes(c, m, metas)
+        torch.cuda.synchronize()
+        t_acc += time.perf_counter() - t0
+    gpu_ms = 1e3 * t_acc / (reps * len(metas))
     out = {"what": "get_bboxes: 2 x 100 mask upsample+threshold to 800x1333, panoptic argmax/areas, labels, rel dists",
            "gpu_ms_per_image": gpu_ms, "segments_kept": int((res[0][4] // 1000).unique().numel()),
            "timing": "host wall clock incl. the per-pass area D2H (post-processing is host-driven in the reference too)"}

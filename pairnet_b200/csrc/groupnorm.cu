@@ -62,23 +62,30 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_nchw_kernel(const float* 
   }
 }
 // ---- pass 1b: reduce partials -> per (b, c) scale/shift:  y = x * scale + shift -----------------------------
-__global__ void gn_finalize_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale_shift, int groups, int nchunk,
-                                   double count, float eps) {
-  const int b = blockIdx.x, c = threadIdx.x;  // 256 threads
-  const int cpg = D / groups, g = c / cpg;
+// one warp per (image, group): lanes stride over the per-CTA partials, shuffle-reduce in double, then the group's
+// channels (cpg <= 32) get their scale / shift
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ scale_shift,
+                                                          int B, int groups, int nchunk, double count, float eps) {
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= B * groups) return;
+  const int b = wid / groups, g = wid - b * groups;
+  const double* p = part + (size_t)wid * nchunk * 2;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    s += part[(((size_t)b * groups + g) * nchunk + k) * 2 + 0];
-    q += part[(((size_t)b * groups + g) * nchunk + k) * 2 + 1];
-  }
+  for (int k = lane; k < nchunk; k += 32) { s += p[2 * k]; q += p[2 * k + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
   const double mean = s / count;
   double var = q / count - mean * mean;
   var = var < 0.0 ? 0.0 : var;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = rstd * __ldg(gamma + c);
-  scale_shift[((size_t)b * D + c) * 2 + 0] = sc;
-  scale_shift[((size_t)b * D + c) * 2 + 1] = __ldg(beta + c) - (float)mean * sc;
+  const int cpg = D / groups;
+  for (int j = lane; j < cpg; j += 32) {
+    const int c = g * cpg + j;
+    const float sc = rstd * __ldg(gamma + c);
+    scale_shift[((size_t)b * D + c) * 2 + 0] = sc;
+    scale_shift[((size_t)b * D + c) * 2 + 1] = __ldg(beta + c) - (float)mean * sc;
+  }
 }
 // ---- pass 2: apply --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_apply_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ ss,
@@ -203,7 +210,7 @@ int pn_group_norm(const float* x, const float* gamma, const float* beta, float* 
     gn_stats_nchw_kernel<<<dim3(nchunk, B * groups), GN_THREADS, 0, st>>>(x, part, (long long)HW * (D / groups), nchunk);
     PN_TRY(check_launch("gn_stats_nchw_kernel"));
   }
-  gn_finalize_kernel<<<B, D, 0, st>>>(part, gamma, beta, ss, groups, nchunk, count, eps);
+  gn_finalize_kernel<<<cdiv(B * groups, 8), 256, 0, st>>>(part, gamma, beta, ss, B, groups, nchunk, count, eps);
   PN_TRY(check_launch("gn_finalize_kernel"));
   if (channels_last) {
     const long long n4 = (long long)B * HW * (D / 4);
@@ -246,7 +253,7 @@ int pn_gn_upsample_add(const float* x, const float* gamma, const float* beta, co
   float* ss = reinterpret_cast<float*>(part + (size_t)B * groups * nchunk * 2);
   gn_stats_nhwc_kernel<<<dim3(nchunk, B), GN_THREADS, 0, st>>>(x, part, HW, cdiv(HW, nchunk), groups, nchunk);
   PN_TRY(check_launch("gn_stats_nhwc_kernel"));
-  gn_finalize_kernel<<<B, D, 0, st>>>(part, gamma, beta, ss, groups, nchunk, (double)HW * (D / groups), eps);
+  gn_finalize_kernel<<<cdiv(B * groups, 8), 256, 0, st>>>(part, gamma, beta, ss, B, groups, nchunk, (double)HW * (D / groups), eps);
   PN_TRY(check_launch("gn_finalize_kernel"));
   const long long n4 = (long long)B * HW * (D / 4);
   gn_apply_upadd_nhwc_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, ss, top, top_batch_stride, y, n4, H, W, h, w,
