@@ -562,7 +562,16 @@ static int ppn_forward(const float* query, const float* query_obj, const PnMlp3*
     // large batches (micro-benchmark 5a): walk the batch in chunks whose pair matrices stay resident in the 126 MB
     // L2 between the kernel that writes them and the top-k kernel that reads them back
     int cb = (int)(PPN_L2_CHUNK_BYTES / img_bytes);
-    cb = cb < 1 ? 1 : cb;
+    // the top-k kernel runs one CTA per image: never hand it less than one wave of SMs (N = 400: 75 images fit the L2
+    // budget, which left half of the 148 SMs idle), even if part of the chunk then spills to HBM
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (num_sms <= 0) num_sms = 148;
+    }
+    cb = cb < num_sms ? num_sms : cb;
     for (int b0 = 0; b0 < B; b0 += cb) {
       const int nb = B - b0 < cb ? B - b0 : cb;
       PN_TRY(pair_matrix(S + (size_t)b0 * N * D, O + (size_t)b0 * N * D, importance + (size_t)b0 * N * N, nb));
