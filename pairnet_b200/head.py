@@ -167,6 +167,15 @@ class CrossHead2(nn.Module):
                                         img_metas[i]["scale_factor"], rescale)
                 for i in range(len(img_metas))]
 
+    @staticmethod
+    def _stuff_remap(labels, first_stuff_label=80):
+        """pairnet_head.py:858-861 + :877-882: kept segments of the same stuff class (label >= 80) are merged into the
+        first of them.  Returns ``remap`` with ``remap[k]`` = position (in the kept list) segment ``k`` is painted as."""
+        first, remap = {}, []
+        for k, lab in enumerate(labels):
+            remap.append(first.setdefault(lab, k) if lab >= first_stuff_label else k)
+        return remap
+
     @torch.no_grad()
     def _get_bboxes_single(self, all_masks, all_cls_score, s_cls_score, o_cls_score, r_cls_score, s_mask_pred,
                            o_mask_pred, img_shape, scale_factor, rescale=False):
@@ -216,11 +225,7 @@ class CrossHead2(nn.Module):
                                                 area.data_ptr(), stream), "pn_panoptic_merge")
                 return area.tolist()  # one small D2H per pass (the reference does one .item() per mask)
 
-            # stuff classes (label >= 80) seen more than once are merged into their first instance (:858-861, :877-882)
-            first, remap = {}, []
-            for k, lab in enumerate(labels_k.tolist()):
-                remap.append(first.setdefault(lab, k) if lab >= 80 else k)
-            area = merge(keep_idx, labels_k, remap)
+            area = merge(keep_idx, labels_k, self._stuff_remap(labels_k.tolist()))
             while True:  # drop segments of <= 4 pixels and re-run the argmax without them (:896-908)
                 small = torch.tensor([a <= 4 for a in area], dtype=torch.bool, device=dev)
                 if not bool(small.any()):

@@ -64,6 +64,29 @@ def test_result_container_and_triplet2result():
         Result(no_such_field=1)
 
 
+def test_stuff_remap_host_logic_matches_reference_masked_fill_semantics():
+    """CPU: the remap table handed to ``pn_panoptic_merge`` vs the reference's in-place ``masked_fill_`` loop."""
+    from collections import defaultdict
+    from pairnet_b200.head import CrossHead2
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = int(rng.integers(1, 40))
+        labels = rng.integers(60, 100, n).tolist()
+        m_id = torch.from_numpy(rng.integers(0, n, (6, 7)))
+        equiv = defaultdict(list)
+        for k, lab in enumerate(labels):
+            if lab >= 80:
+                equiv[lab].append(k)
+        ref = m_id.clone()
+        for e in equiv.values():
+            if len(e) > 1:
+                for eq_id in e:
+                    ref.masked_fill_(ref.eq(eq_id), e[0])
+        remap = torch.tensor(CrossHead2._stuff_remap(labels))
+        assert torch.equal(remap[m_id], ref)
+    assert CrossHead2._stuff_remap([3, 85, 85, 90, 3, 85]) == [0, 1, 1, 3, 4, 1]
+
+
 def _product_head(N, K):
     from oracle.head import HeadHyper, OCrossHead2
     from oracle.weights import fixture_state_dict
