@@ -62,12 +62,6 @@ static int side_wait(cudaStream_t who, cudaEvent_t e) {
   return 0;
 }
 
-static int memset_async(void* p, int v, size_t bytes, cudaStream_t st) {
-  ++g_launches;
-  cudaError_t e = cudaMemsetAsync(p, v, bytes, st);
-  if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  return 0;
-}
 static int copy_async(void* d, const void* s, size_t bytes, cudaStream_t st) {
   ++g_launches;
   cudaError_t e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st);

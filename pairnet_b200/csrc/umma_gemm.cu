@@ -87,7 +87,6 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
 template <int BN, int NUM_EPI_WARPS, bool A_RAW>
 __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? 128 : 0), 1)
 umma_gemm_kernel(const __grid_constant__ Params prm) {
-  constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + (A_RAW ? 128 : 0);
   constexpr int STAGES = A_RAW ? 4 : Cfg<BN>::STAGES;
   constexpr int B_TILE = Cfg<BN>::B_TILE_BYTES;
   constexpr int STAGE_BYTES = A_RAW ? (A_TILE_BYTES + 2 * B_TILE) : Cfg<BN>::STAGE_BYTES;
