@@ -49,10 +49,29 @@ class PSGTr(nn.Module):
         results_list = self.bbox_head.simple_test(feat, img_metas, rescale=rescale)
         return [triplet2Result(triplets, self.bbox_head.use_mask) for triplets in results_list]
 
-    def forward(self, img, img_metas=None, return_loss=False, **kwargs):
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """mmdet ``BaseDetector.forward_test``: ``imgs`` / ``img_metas`` are lists over test-time augmentations (what
+        ``single_gpu_test`` passes: ``model(return_loss=False, rescale=True, **data)``, reference ``tools/test.py:250-267``)."""
+        for var, name in ((imgs, "imgs"), (img_metas, "img_metas")):
+            if not isinstance(var, (list, tuple)):
+                raise TypeError(f"{name} must be a list, but got {type(var)}")
+        if len(imgs) != len(img_metas):
+            raise ValueError(f"num of augmentations ({len(imgs)}) != num of image meta ({len(img_metas)})")
+        for img, metas in zip(imgs, img_metas):
+            for meta in metas:
+                meta.setdefault("batch_input_shape", tuple(img.shape[-2:]))
+        if len(imgs) == 1:
+            return self.simple_test(imgs[0], img_metas[0], **kwargs)
+        raise NotImplementedError("test-time augmentation (aug_test) is not provided by the reference detector either")
+
+    def forward(self, img, img_metas=None, return_loss=True, **kwargs):
+        """mmdet ``BaseDetector.forward``: ``return_loss=True`` -> ``forward_train``; otherwise ``forward_test`` on the
+        augmentation lists.  A bare tensor with no metas is the ``forward_dummy`` call (FLOPs tools, ``bench.py``)."""
+        if img_metas is None and torch.is_tensor(img):
+            return self.forward_dummy(img)
         if return_loss:
             return self.forward_train(img, img_metas, **kwargs)
-        return self.forward_dummy(img)
+        return self.forward_test(img, img_metas, **kwargs)
 
 
 class GraphedForward:

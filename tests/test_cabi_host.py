@@ -132,3 +132,35 @@ def test_constructor_asserts_mirror_reference():
     cfg["positional_encoding"] = dict(type="SinePositionalEncoding", num_feats=64, normalize=True)
     with pytest.raises(AssertionError):
         build_head(cfg)  # pairnet_head.py:74-78
+
+
+def test_detector_forward_dispatch_mirrors_mmdet_base_detector():
+    """Host logic only (no kernels): ``PSGTr.forward`` routes like mmdet's ``BaseDetector.forward`` -- the call
+    ``tools/test.py`` makes is ``model(return_loss=False, rescale=True, img=[tensor], img_metas=[[dict, ...]])``."""
+    from pairnet_b200.detector import PSGTr
+    calls = []
+
+    class Stub(PSGTr):
+        def __init__(self):  # no backbone / head: dispatch only
+            torch.nn.Module.__init__(self)
+
+        def simple_test(self, img, img_metas, rescale=False):
+            calls.append(("simple_test", tuple(img.shape), len(img_metas), rescale, img_metas[0]["batch_input_shape"]))
+            return ["r"] * len(img_metas)
+
+        def forward_dummy(self, img):
+            calls.append(("forward_dummy", tuple(img.shape)))
+            return "d"
+
+    m = Stub()
+    img = torch.zeros(2, 3, 8, 12)
+    metas = [dict(img_shape=(8, 12, 3)), dict(img_shape=(8, 12, 3))]
+    assert m(return_loss=False, rescale=True, img=[img], img_metas=[metas]) == ["r", "r"]
+    assert calls[-1] == ("simple_test", (2, 3, 8, 12), 2, True, (8, 12))
+    assert m(img) == "d" and calls[-1] == ("forward_dummy", (2, 3, 8, 12))
+    with pytest.raises(TypeError):
+        m(img, metas, return_loss=False)            # not wrapped in augmentation lists
+    with pytest.raises(NotImplementedError):
+        m([img, img], [metas, metas], return_loss=False)   # aug_test
+    with pytest.raises(NotImplementedError):
+        m(img, metas, return_loss=True)             # training: SURVEY 8f rank 2
