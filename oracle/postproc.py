@@ -17,10 +17,11 @@ import torch.nn.functional as F
 INSTANCE_OFFSET = 1000  # mmdet.datasets.coco_panoptic.INSTANCE_OFFSET
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-POST_CASES = [  # (tag, B, N, K, (h4, w4), img_shape (H, W), scale_factor, seed)
+POST_CASES = [  # (tag, B, N, K, (h4, w4), img_shape (H, W), scale_factor, seed[, confident])
     ("b2_24x40", 2, 100, 100, (24, 40), (96, 160), (1.0, 1.0), 31),
     ("b1_32x48_scaled", 1, 100, 100, (32, 48), (128, 192), (1.6, 1.6), 32),
     ("b1_20x28_n40", 1, 40, 24, (20, 28), (80, 111), (1.0, 1.0), 33),
+    ("b1_16x24_nothing_kept", 1, 40, 24, (16, 24), (64, 96), (1.0, 1.0), 34, False),  # no query passes score > 0.5
 ]
 
 
@@ -93,7 +94,7 @@ def get_bboxes(cls_scores, mask_preds, img_metas, num_relations, num_rel_query):
 
 
 # ------------------------------------------------------------------------------------------------ synthetic outputs
-def synthetic_head_outputs(B, N, K, hw4, seed, num_classes=133, num_relations=56):
+def synthetic_head_outputs(B, N, K, hw4, seed, num_classes=133, num_relations=56, confident=True):
     """Head outputs with the structure post-processing branches on: confident thing / stuff / background queries,
     duplicated stuff classes (dedup path), smooth mask logits plus a few needle masks that win <= 4 pixels (small-area
     filter loop).  Deterministic (numpy PCG64)."""
@@ -101,7 +102,7 @@ def synthetic_head_outputs(B, N, K, hw4, seed, num_classes=133, num_relations=56
     h, w = hw4
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     cls = rng.standard_normal((B, N, num_classes + 1))
-    for b in range(B):
+    for b in range(B if confident else 0):
         conf = rng.permutation(N)[: max(6, N // 3)]
         for j, q in enumerate(conf):
             c = [85, 85, 120, 3, 17, num_classes][j] if j < 6 else int(rng.integers(0, num_classes + 1))
@@ -110,7 +111,7 @@ def synthetic_head_outputs(B, N, K, hw4, seed, num_classes=133, num_relations=56
     lo = rng.standard_normal((B, N, (h + 3) // 4, (w + 3) // 4)) * 4.0
     mask = F.interpolate(f32(lo), size=(h, w), mode="bicubic", align_corners=False).numpy().astype(np.float64)
     mask += rng.standard_normal((B, N, h, w)) * 0.3
-    for b in range(B):  # needle masks: strongly negative except one pixel
+    for b in range(B if confident else 0):  # needle masks: strongly negative except one pixel
         for q in rng.permutation(N)[:3]:
             mask[b, q] = -30.0
             mask[b, q, int(rng.integers(0, h)), int(rng.integers(0, w))] = 40.0
@@ -127,8 +128,8 @@ def synthetic_head_outputs(B, N, K, hw4, seed, num_classes=133, num_relations=56
 
 
 def case_inputs(case):
-    tag, B, N, K, hw4, img_shape, sf, seed = case
-    cls_scores, mask_preds, sp, op = synthetic_head_outputs(B, N, K, hw4, seed)
+    tag, B, N, K, hw4, img_shape, sf, seed = case[:8]
+    cls_scores, mask_preds, sp, op = synthetic_head_outputs(B, N, K, hw4, seed, confident=case[8] if len(case) > 8 else True)
     H, W = img_shape
     metas = [dict(img_shape=(int(round(H * sf[1])), int(round(W * sf[0])), 3),
                   scale_factor=np.array([sf[0], sf[1], sf[0], sf[1]], dtype=np.float32)) for _ in range(B)]
