@@ -40,6 +40,7 @@ REF_CASES = [  # (tag, B, (H4,W4) of mask_feature, seed, N obj queries, R rel qu
     ("b2_32x48", 2, (32, 48), 21, 100, 100),
     ("b1_40x56", 1, (40, 56), 22, 100, 100),
     ("b3_24x40_n40_r24", 3, (24, 40), 23, 40, 24),
+    ("b1_32x32_n200_r200", 1, (32, 32), 24, 200, 200),   # BASELINE config 4's query count
 ]
 
 

@@ -303,7 +303,9 @@ def test_channels_last_mask_features_and_mask_tc_option(heads):
 
 def _ref_cases():
     from oracle.pin_reference import REF_CASES
-    return REF_CASES
+    # the 200-query fixture pins the ORACLE to the reference (CPU tests); on the GPU the 200-query head is compared with
+    # the oracle directly (test_head_other_query_counts_and_batches), without the <= 4 near-tie swap allowance used here
+    return [c for c in REF_CASES if c[4] <= 100]
 
 
 @pytest.mark.parametrize("tag,B,hw4,seed,N,R", _ref_cases())
