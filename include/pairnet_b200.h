@@ -90,6 +90,8 @@ PN_API int pn_get_option(int key);
                                  * operands split in the SM); 0 = exact-fp32 FFMA */
 #define PN_OPT_MASK_TC 9        /* default 1: mask einsums (attention-mask bits, final mask_pred) on the tcgen05 GEMM with
                                    token-major operands; 0 = FFMA kernels on NCHW / N-major operands */
+#define PN_OPT_FUSED_CHAIN 10    /* default 1: decoders whose weights carry a prepared blob (pn_*_prepare) run their query-side
+                                   layers as ONE cluster launch of the fused tcgen05 chain kernel (chain.cu); 0 = per-op kernels */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */
@@ -189,6 +191,7 @@ typedef struct {
   PnLinear cls_embed;         /* [num_cls,256] */
   PnMlp3 mask_embed;
   PnDecoderLayer layers[PN_MAX_LAYERS];
+  const void* prepared;       /* optional: blob built by pn_m2f_prepare (static hi/lo weight splits); NULL = split per forward */
 } PnM2FWeights;
 
 typedef struct {
@@ -253,7 +256,17 @@ typedef struct {
   const float* rel_query_embed2; /* [2K,256] key_pos   (rel_query_embed3 is dead in the reference) */
   PnLinear rel_cls_embed;        /* [num_rel_cls,256] */
   PnDecoderLayer layers[PN_MAX_LAYERS];
+  const void* prepared;          /* optional: blob built by pn_rel_prepare; NULL = per-op kernels, nothing cached */
 } PnRelWeights;
+
+/* Prepared weights.  The tensor-core kernels consume every weight matrix as a TF32 hi/lo pair (3xTF32, fp32 parity).
+ * Weights are static between optimiser steps, so the pairs (plus the per-stage concatenations the fused kernels
+ * read) are built ONCE into a caller-owned device buffer and referenced from PnRelWeights.prepared /
+ * PnM2FWeights.prepared.  Re-run after the weights change.  `w->prepared` itself is ignored by these calls. */
+PN_API size_t pn_rel_prepared_bytes(const PnRelWeights* w);
+PN_API int pn_rel_prepare(const PnRelWeights* w, void* prepared, size_t bytes, pn_stream_t stream);
+PN_API size_t pn_m2f_prepared_bytes(const PnM2FWeights* w);
+PN_API int pn_m2f_prepare(const PnM2FWeights* w, void* prepared, size_t bytes, pn_stream_t stream);
 
 PN_API size_t pn_relation_fusion_workspace_bytes(int B, int R, int K2, int ffn_dims);
 PN_API int pn_relation_fusion_forward(const PnRelWeights* w, const float* pair_feat /* [B,K2,256] */,

@@ -45,7 +45,7 @@ class PnM2FWeights(C.Structure):
     _fields_ = [("num_queries", C.c_int), ("num_layers", C.c_int), ("num_levels", C.c_int), ("ffn_dims", C.c_int),
                 ("num_cls", C.c_int), ("query_feat", c_void_p), ("query_embed", c_void_p), ("level_embed", c_void_p),
                 ("post_norm", PnNorm), ("cls_embed", PnLinear), ("mask_embed", PnMlp3),
-                ("layers", PnDecoderLayer * PN_MAX_LAYERS)]
+                ("layers", PnDecoderLayer * PN_MAX_LAYERS), ("prepared", c_void_p)]
 
 
 class PnM2FInputs(C.Structure):
@@ -64,7 +64,7 @@ class PnM2FOutputs(C.Structure):
 class PnRelWeights(C.Structure):
     _fields_ = [("num_rel_queries", C.c_int), ("num_layers", C.c_int), ("ffn_dims", C.c_int), ("num_rel_cls", C.c_int),
                 ("rel_query_feat", c_void_p), ("rel_query_embed", c_void_p), ("rel_query_embed2", c_void_p),
-                ("rel_cls_embed", PnLinear), ("layers", PnDecoderLayer * PN_MAX_LAYERS)]
+                ("rel_cls_embed", PnLinear), ("layers", PnDecoderLayer * PN_MAX_LAYERS), ("prepared", c_void_p)]
 
 
 class PnHeadWeights(C.Structure):
@@ -94,7 +94,7 @@ i32, i64, sz, vp = C.c_int, C.c_longlong, C.c_size_t, c_void_p
 P = C.POINTER
 
 # name -> (restype, argtypes); every symbol declared in include/pairnet_b200.h
-PN_OPT_TENSOR_CORES, PN_OPT_OVERLAP, PN_OPT_SKINNY, PN_OPT_MASK_TC = 0, 3, 8, 9  # include/pairnet_b200.h
+PN_OPT_TENSOR_CORES, PN_OPT_OVERLAP, PN_OPT_SKINNY, PN_OPT_MASK_TC, PN_OPT_FUSED_CHAIN = 0, 3, 8, 9, 10  # include/pairnet_b200.h
 
 SIGNATURES = {
     "pn_version": (i32, []),
@@ -132,6 +132,10 @@ SIGNATURES = {
                              vp, sz, vp]),
     "pn_conv_tiny": (i32, [vp, P(PnConvTiny), vp, i32, i32, vp, sz, vp]),
     "pn_topk_pairs": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "pn_rel_prepared_bytes": (sz, [P(PnRelWeights)]),
+    "pn_rel_prepare": (i32, [P(PnRelWeights), vp, sz, vp]),
+    "pn_m2f_prepared_bytes": (sz, [P(PnM2FWeights)]),
+    "pn_m2f_prepare": (i32, [P(PnM2FWeights), vp, sz, vp]),
     "pn_relation_fusion_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "pn_relation_fusion_forward": (i32, [P(PnRelWeights), vp, vp, vp, i32, i32, vp, sz, vp]),
     "pn_gather_rows": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),

@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -229,6 +229,47 @@ static int mask_pred_tc(const float* e, float* eh, float* el, const float* Ftok,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Prepared weights (pn_rel_prepare / pn_m2f_prepare): static TF32 hi/lo splits, carved from a caller-owned blob.
+struct PreparedLayer {
+  float *cin_hi, *cin_lo, *co_hi, *co_lo, *sin_hi, *sin_lo, *so_hi, *so_lo, *f1_hi, *f1_lo, *f2_hi, *f2_lo;
+};
+static void carve_layer(Workspace& ws, int ffn, PreparedLayer& L) {
+  L.cin_hi = ws.take<float>((size_t)3 * D * D); L.cin_lo = ws.take<float>((size_t)3 * D * D);
+  L.co_hi = ws.take<float>((size_t)D * D); L.co_lo = ws.take<float>((size_t)D * D);
+  L.sin_hi = ws.take<float>((size_t)3 * D * D); L.sin_lo = ws.take<float>((size_t)3 * D * D);
+  L.so_hi = ws.take<float>((size_t)D * D); L.so_lo = ws.take<float>((size_t)D * D);
+  L.f1_hi = ws.take<float>((size_t)ffn * D); L.f1_lo = ws.take<float>((size_t)ffn * D);
+  L.f2_hi = ws.take<float>((size_t)ffn * D); L.f2_lo = ws.take<float>((size_t)ffn * D);
+}
+static int prepare_layer(const PnDecoderLayer& w, int ffn, const PreparedLayer& L, cudaStream_t st) {
+  PN_TRY(launch_split_tf32(w.cross_attn.in_proj_w, L.cin_hi, L.cin_lo, (size_t)3 * D * D, st));
+  PN_TRY(launch_split_tf32(w.cross_attn.out_proj_w, L.co_hi, L.co_lo, (size_t)D * D, st));
+  PN_TRY(launch_split_tf32(w.self_attn.in_proj_w, L.sin_hi, L.sin_lo, (size_t)3 * D * D, st));
+  PN_TRY(launch_split_tf32(w.self_attn.out_proj_w, L.so_hi, L.so_lo, (size_t)D * D, st));
+  PN_TRY(launch_split_tf32(w.ffn1.w, L.f1_hi, L.f1_lo, (size_t)ffn * D, st));
+  return launch_split_tf32(w.ffn2.w, L.f2_hi, L.f2_lo, (size_t)ffn * D, st);
+}
+static void chain_layer_fill(ChainLayer& c, const PnDecoderLayer& w, const PreparedLayer& L) {
+  c.cin_hi = L.cin_hi; c.cin_lo = L.cin_lo; c.co_hi = L.co_hi; c.co_lo = L.co_lo; c.sin_hi = L.sin_hi; c.sin_lo = L.sin_lo;
+  c.so_hi = L.so_hi; c.so_lo = L.so_lo; c.f1_hi = L.f1_hi; c.f1_lo = L.f1_lo; c.f2_hi = L.f2_hi; c.f2_lo = L.f2_lo;
+  c.cin_b = w.cross_attn.in_proj_b; c.co_b = w.cross_attn.out_proj_b; c.sin_b = w.self_attn.in_proj_b;
+  c.so_b = w.self_attn.out_proj_b; c.f1_b = w.ffn1.b; c.f2_b = w.ffn2.b;
+  for (int i = 0; i < 3; ++i) { c.gamma[i] = w.norm[i].gamma; c.beta[i] = w.norm[i].beta; }
+}
+
+struct PreparedM2F {
+  PreparedLayer L[PN_MAX_LAYERS];
+  float *me_hi[3], *me_lo[3];  // mask_embed MLP [256,256] x3
+};
+static void carve_m2f(Workspace& ws, const PnM2FWeights* w, PreparedM2F& p) {
+  for (int l = 0; l < w->num_layers; ++l) carve_layer(ws, w->ffn_dims, p.L[l]);
+  for (int i = 0; i < 3; ++i) {
+    p.me_hi[i] = ws.take<float>((size_t)D * D);
+    p.me_lo[i] = ws.take<float>((size_t)D * D);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct M2FPlan {
   int B, N, M, L, nl, ffn;
   int hw[PN_MAX_LEVELS], ldf[PN_MAX_LEVELS];
@@ -346,6 +387,12 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
     b.teh = tail->eh; b.tel = tail->el; b.Ftok = tail->ftok;
   }
   const bool tcm = p.tc_mask;
+  PreparedM2F prep{};
+  const bool have_prep = w->prepared != nullptr;
+  if (have_prep) {
+    Workspace pw(const_cast<void*>(w->prepared), (size_t)1 << 60);
+    carve_m2f(pw, w, prep);
+  }
   const float* Ftok = nullptr;  // mask_features as [B,HW4,256]
   if (tcm) {
     Ftok = in->mask_features;
@@ -410,7 +457,12 @@ static int m2f_forward(const PnM2FWeights* w, const PnM2FInputs* in, const PnM2F
       // tcgen05 path: TMA-staged tiles, UMMA kind::tf32 with hi/lo split operands (fp32 parity)
       float* Whi = b.Whi + (size_t)i * 2 * D * D;
       float* Wlo = b.Wlo + (size_t)i * 2 * D * D;
-      PN_TRY(launch_split_tf32(Lw.cross_attn.in_proj_w + (size_t)D * D, Whi, Wlo, (size_t)2 * D * D, s2));
+      if (have_prep) {  // static [Wk;Wv] splits from the prepared blob (rows 256..767 of in_proj)
+        Whi = prep.L[i].cin_hi + (size_t)D * D;
+        Wlo = prep.L[i].cin_lo + (size_t)D * D;
+      } else {
+        PN_TRY(launch_split_tf32(Lw.cross_attn.in_proj_w + (size_t)D * D, Whi, Wlo, (size_t)2 * D * D, s2));
+      }
       UmmaOperand o[2] = {
           {b.XP[l], b.XPlo[l], D, Whi, Wlo, D, Lw.cross_attn.in_proj_b + D, Kc, D, Mk, D, D},
           {b.X[l], b.Xlo[l], D, Whi + (size_t)D * D, Wlo + (size_t)D * D, D, Lw.cross_attn.in_proj_b + 2 * D, Vc, D, Mk, D,
@@ -594,6 +646,108 @@ static size_t ppn_bytes(int B, int N, int K, int mid) {
 }
 
 // ------------------------------------------------------------------------------------------------
+struct PreparedRel {
+  PreparedLayer L[PN_MAX_LAYERS];
+  float *ck_hi, *ck_lo, *cv_hi, *cv_lo;  // [nl*256,256]: cross-attention Wk / Wv of all layers, concatenated
+  float *bk, *bv;                        // [nl*256]
+  float *cls_hi, *cls_lo;                // [num_rel_cls,256]
+};
+static void carve_rel(Workspace& ws, const PnRelWeights* w, PreparedRel& p) {
+  const int nl = w->num_layers;
+  for (int l = 0; l < nl; ++l) carve_layer(ws, w->ffn_dims, p.L[l]);
+  p.ck_hi = ws.take<float>((size_t)nl * D * D); p.ck_lo = ws.take<float>((size_t)nl * D * D);
+  p.cv_hi = ws.take<float>((size_t)nl * D * D); p.cv_lo = ws.take<float>((size_t)nl * D * D);
+  p.bk = ws.take<float>((size_t)nl * D); p.bv = ws.take<float>((size_t)nl * D);
+  p.cls_hi = ws.take<float>((size_t)w->num_rel_cls * D); p.cls_lo = ws.take<float>((size_t)w->num_rel_cls * D);
+}
+static bool rel_fused_ok(const PnRelWeights* w) {
+  return w->prepared && get_option(OPT_FUSED_CHAIN) && get_option(OPT_TENSOR_CORES) && w->num_layers <= CHAIN_MAX_LAYERS &&
+         w->ffn_dims % 1024 == 0 && w->num_rel_cls <= 128 && w->num_rel_cls % 4 == 0;
+}
+
+struct RelFusedBufs {
+  float *x, *xpos, *pk, *p_hi, *p_lo, *kc_hi, *kc_lo, *vtc_hi, *vtc_lo, *scratch;
+};
+static void rel_take_fused(Workspace& ws, int B, int R, int K2, int nl, int ffn, RelFusedBufs& b) {
+  const size_t M = (size_t)B * R, Mk = (size_t)B * K2;
+  const size_t ldvc = (size_t)round_up(K2, 4);
+  b.x = ws.take<float>(M * D); b.xpos = ws.take<float>(M * D);
+  b.pk = ws.take<float>(Mk * D); b.p_hi = ws.take<float>(Mk * D); b.p_lo = ws.take<float>(Mk * D);
+  b.kc_hi = ws.take<float>(Mk * nl * D); b.kc_lo = ws.take<float>(Mk * nl * D);
+  b.vtc_hi = ws.take<float>((size_t)B * nl * D * ldvc); b.vtc_lo = ws.take<float>((size_t)B * nl * D * ldvc);
+  b.scratch = ws.take<float>(chain_scratch_floats(B, R, ffn));
+}
+// carve the chain kernel's scratch (layout of chain_scratch_floats)
+static void chain_carve(float* s, int B, int R, int ffn, ChainArgs& a) {
+  const size_t M = (size_t)B * R, MD = M * D;
+  const size_t ldvs = (size_t)round_up(R, 4);
+  a.x1 = s; s += MD; a.x1pos = s; s += MD; a.x2 = s; s += MD; a.pre = s; s += MD; a.att = s; s += MD;
+  a.h = s; s += M * ffn; a.parts = s; s += 8 * MD;
+  a.q_hi = s; s += MD; a.q_lo = s; s += MD; a.ks_hi = s; s += MD; a.ks_lo = s; s += MD;
+  a.vts_hi = s; s += (size_t)B * D * ldvs; a.vts_lo = s; s += (size_t)B * D * ldvs;
+  a.ldvs = (int)ldvs;
+}
+
+// Relation Fusion (pairnet_head.py:353-378) on the fused chain: 5 launches in front (key-side operands of all
+// layers on the tcgen05 GEMM), then ONE cluster launch for the six layers + the relation classifier.
+static int rel_forward_fused(const PnRelWeights* w, const float* pair_feat, float* rel_preds, float* rel_feat_out, int B,
+                             int K2, Workspace& ws, cudaStream_t st) {
+  const int R = w->num_rel_queries, nl = w->num_layers, ffn = w->ffn_dims;
+  PreparedRel P;
+  {
+    Workspace pw(const_cast<void*>(w->prepared), (size_t)1 << 60);
+    carve_rel(pw, w, P);
+  }
+  RelFusedBufs b;
+  rel_take_fused(ws, B, R, K2, nl, ffn, b);
+  PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "relation_fusion: workspace too small");
+  const int Mk = B * K2, ldk = nl * D;
+  const int ldvc = (int)round_up(K2, 4);
+  PN_TRY(launch_add_rows(pair_feat, w->rel_query_embed2, b.pk, B, K2, st));
+  PN_TRY(launch_split_tf32(pair_feat, b.p_hi, b.p_lo, (size_t)Mk * D, st));
+  // K of every layer: [Mk, nl*256] = (pair + key_pos) [Wk_0; ..; Wk_nl-1]^T, emitted split hi/lo (column chunks <= 1024)
+  {
+    UmmaOperand o[4];
+    int n = 0;
+    for (int n0 = 0; n0 < ldk; n0 += 1024) {
+      const int nc = ldk - n0 < 1024 ? ldk - n0 : 1024;
+      UmmaOperand k{b.pk, nullptr, D, P.ck_hi + (size_t)n0 * D, P.ck_lo + (size_t)n0 * D, D, P.bk + n0, b.kc_hi + n0, ldk, Mk,
+                    nc, D};
+      k.C_lo = b.kc_lo + n0;
+      k.a_is_raw = 1;
+      o[n++] = k;
+      if (n == 4 || n0 + 1024 >= ldk) { PN_TRY(launch_umma_gemm(o, n, 3, st)); n = 0; }
+    }
+  }
+  // V^T of every layer, per image: [nl*256, K2] = [Wv_0; ..] pair_b^T + bv (weights as the A operand, row chunks <= 1024)
+  {
+    UmmaOperand o[4];
+    int n = 0;
+    for (int bi = 0; bi < B; ++bi)
+      for (int m0 = 0; m0 < ldk; m0 += 1024) {
+        const int mc = ldk - m0 < 1024 ? ldk - m0 : 1024;
+        UmmaOperand v{P.cv_hi + (size_t)m0 * D, P.cv_lo + (size_t)m0 * D, D, b.p_hi + (size_t)bi * K2 * D,
+                      b.p_lo + (size_t)bi * K2 * D, D, P.bv + m0, b.vtc_hi + ((size_t)bi * ldk + m0) * ldvc, ldvc, mc, K2, D};
+        v.C_lo = b.vtc_lo + ((size_t)bi * ldk + m0) * ldvc;
+        v.bias_per_row = 1;
+        o[n++] = v;
+        const bool last = bi == B - 1 && m0 + 1024 >= ldk;
+        if (n == 4 || last) { PN_TRY(launch_umma_gemm(o, n, 3, st)); n = 0; }
+      }
+  }
+  ChainArgs a{};
+  for (int l = 0; l < nl; ++l) chain_layer_fill(a.layers[l], w->layers[l], P.L[l]);
+  chain_carve(b.scratch, B, R, ffn, a);
+  a.x = b.x; a.xpos = b.xpos;
+  a.kc_hi = b.kc_hi; a.kc_lo = b.kc_lo; a.vtc_hi = b.vtc_hi; a.vtc_lo = b.vtc_lo;
+  a.init_feat = w->rel_query_feat; a.qpos = w->rel_query_embed;
+  a.cls_hi = P.cls_hi; a.cls_lo = P.cls_lo; a.cls_b = w->rel_cls_embed.b; a.cls_out = rel_preds;
+  a.B = B; a.R = R; a.Nk = K2; a.nl = nl; a.ffn = ffn; a.ncls = w->num_rel_cls; a.ldvc = ldvc; a.has_cross_attn = 1;
+  PN_TRY(launch_decoder_chain(a, st));
+  if (rel_feat_out) PN_TRY(copy_async(rel_feat_out, b.x, sizeof(float) * (size_t)B * R * D, st));
+  return 0;
+}
+
 static void rel_take(Workspace& ws, int B, int R, int K2, int nl, int ffn, float** x, float** xpos, float** pk,
                      float** Kall, float** Vall, LayerScratch& ls) {
   const int M = B * R, Mk = B * K2;
@@ -612,6 +766,7 @@ static int rel_forward(const PnRelWeights* w, const float* pair_feat, float* rel
   PN_REQUIRE(w && pair_feat && rel_preds, PN_ERR_BAD_ARG, "relation_fusion: null pointer");
   const int R = w->num_rel_queries, nl = w->num_layers, ffn = w->ffn_dims;
   PN_REQUIRE(R > 0 && K2 > 0 && B > 0 && nl >= 1 && nl <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "relation_fusion: bad sizes");
+  if (rel_fused_ok(w)) return rel_forward_fused(w, pair_feat, rel_preds, rel_feat_out, B, K2, ws, st);
   const int M = B * R, Mk = B * K2;
   float *x, *xpos, *pk, *Kall, *Vall;
   LayerScratch ls;
@@ -876,7 +1031,64 @@ size_t pn_relation_fusion_workspace_bytes(int B, int R, int K2, int ffn_dims) {
   float *a, *b, *c, *d, *e;
   LayerScratch ls;
   rel_take(ws, B, R, K2, PN_MAX_LAYERS, ffn_dims, &a, &b, &c, &d, &e, ls);
-  return ws.off + 1024;
+  Workspace wf(nullptr, 0);
+  RelFusedBufs fb;
+  rel_take_fused(wf, B, R, K2, CHAIN_MAX_LAYERS, ffn_dims, fb);
+  return (ws.off > wf.off ? ws.off : wf.off) + 1024;
+}
+
+size_t pn_m2f_prepared_bytes(const PnM2FWeights* w) {
+  if (!w || w->num_layers < 1 || w->num_layers > PN_MAX_LAYERS) return 0;
+  Workspace ws(nullptr, 0);
+  PreparedM2F p;
+  carve_m2f(ws, w, p);
+  return ws.off + 256;
+}
+
+int pn_m2f_prepare(const PnM2FWeights* w, void* prepared, size_t bytes, pn_stream_t stream) {
+  PN_REQUIRE(w && prepared, PN_ERR_BAD_ARG, "m2f_prepare: null argument");
+  PN_REQUIRE(w->num_layers >= 1 && w->num_layers <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "m2f_prepare: bad layer count");
+  PN_REQUIRE(((uintptr_t)prepared & 255) == 0, PN_ERR_BAD_ARG, "m2f_prepare: buffer must be 256-byte aligned");
+  Workspace ws(prepared, bytes);
+  PreparedM2F p;
+  carve_m2f(ws, w, p);
+  PN_REQUIRE(ws.ok(), PN_ERR_WORKSPACE, "m2f_prepare: buffer too small (%zu < %zu)", bytes, ws.off);
+  cudaStream_t st = as_stream(stream);
+  for (int l = 0; l < w->num_layers; ++l) PN_TRY(prepare_layer(w->layers[l], w->ffn_dims, p.L[l], st));
+  for (int i = 0; i < 3; ++i)
+    PN_TRY(launch_split_tf32(w->mask_embed.l[i].w, p.me_hi[i], p.me_lo[i], (size_t)D * D, st));
+  return 0;
+}
+
+size_t pn_rel_prepared_bytes(const PnRelWeights* w) {
+  if (!w || w->num_layers < 1 || w->num_layers > PN_MAX_LAYERS) return 0;
+  Workspace ws(nullptr, 0);
+  PreparedRel p;
+  carve_rel(ws, w, p);
+  return ws.off + 256;
+}
+
+int pn_rel_prepare(const PnRelWeights* w, void* prepared, size_t bytes, pn_stream_t stream) {
+  PN_REQUIRE(w && prepared, PN_ERR_BAD_ARG, "rel_prepare: null argument");
+  PN_REQUIRE(w->num_layers >= 1 && w->num_layers <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "rel_prepare: bad layer count");
+  PN_REQUIRE(((uintptr_t)prepared & 255) == 0, PN_ERR_BAD_ARG, "rel_prepare: buffer must be 256-byte aligned");
+  Workspace ws(prepared, bytes);
+  PreparedRel p;
+  carve_rel(ws, w, p);
+  PN_REQUIRE(ws.ok(), PN_ERR_WORKSPACE, "rel_prepare: buffer too small (%zu < %zu)", bytes, ws.off);
+  cudaStream_t st = as_stream(stream);
+  for (int l = 0; l < w->num_layers; ++l) {
+    PN_TRY(prepare_layer(w->layers[l], w->ffn_dims, p.L[l], st));
+    // [Wk;Wv] = in_proj rows 256..767: concatenate per kind across layers (already split)
+    const size_t blk = (size_t)D * D;
+    PN_TRY(copy_async(p.ck_hi + l * blk, p.L[l].cin_hi + blk, blk * 4, st));
+    PN_TRY(copy_async(p.ck_lo + l * blk, p.L[l].cin_lo + blk, blk * 4, st));
+    PN_TRY(copy_async(p.cv_hi + l * blk, p.L[l].cin_hi + 2 * blk, blk * 4, st));
+    PN_TRY(copy_async(p.cv_lo + l * blk, p.L[l].cin_lo + 2 * blk, blk * 4, st));
+    PN_TRY(copy_async(p.bk + (size_t)l * D, w->layers[l].cross_attn.in_proj_b + D, D * 4, st));
+    PN_TRY(copy_async(p.bv + (size_t)l * D, w->layers[l].cross_attn.in_proj_b + 2 * D, D * 4, st));
+  }
+  return launch_split_tf32(w->rel_cls_embed.w, p.cls_hi, p.cls_lo, (size_t)w->num_rel_cls * D, st);
 }
 
 int pn_relation_fusion_forward(const PnRelWeights* w, const float* pair_feat, float* rel_preds, float* rel_feat_out,

@@ -162,13 +162,44 @@ int launch_split_tf32_scaled(const float* x, float* hi, float* lo, size_t n, flo
 int launch_split_transpose(const float* v, float* vt_hi, float* vt_lo, int B, int Nk, int ldv, cudaStream_t st);
 constexpr float ATTN_QSCALE = 0.17677669529663687f * 1.4426950408889634f;  // (1/sqrt(32)) * log2(e)
 
+// fused decoder chain (chain.cu): whole BaseTransformerLayers in one cluster launch, operands from the prepared blob
+constexpr int CHAIN_MAX_LAYERS = 6;
+struct ChainLayer {  // hi/lo TF32 splits of one layer's weights (row-major, torch layout) + fp32 biases / norms
+  const float *cin_hi, *cin_lo, *co_hi, *co_lo, *sin_hi, *sin_lo, *so_hi, *so_lo, *f1_hi, *f1_lo, *f2_hi, *f2_lo;
+  const float *cin_b, *co_b, *sin_b, *so_b, *f1_b, *f2_b;
+  const float* gamma[3];
+  const float* beta[3];
+};
+struct ChainArgs {
+  ChainLayer layers[CHAIN_MAX_LAYERS];
+  float *x, *xpos;                                   // [B*R,256] in/out (written from init_feat when given)
+  float *pre, *x1, *x1pos, *x2, *att, *h, *parts;    // scratch: [B*R,256] x5, [B*R,ffn], [8][B*R,256]
+  float *q_hi, *q_lo, *ks_hi, *ks_lo;                // [B*R,256]
+  float *vts_hi, *vts_lo;                            // [B*256, ldvs]
+  const float *kc_hi, *kc_lo;                        // cross keys of all layers [B*Nk, nl*256]   (has_cross_attn)
+  const float *vtc_hi, *vtc_lo;                      // cross V^T [B*nl*256, ldvc]
+  const float *init_feat, *qpos;                     // [R,256]
+  const float *cls_hi, *cls_lo, *cls_b;              // final classifier [ncls,256] (cls_out null = none)
+  float* cls_out;
+  // Mask2Former tail: xn = post_norm(x), e = mask_embed(xn) split hi/lo, q of the next layer's cross-attention
+  float *xn, *e1, *e2, *e_hi, *e_lo;
+  const float *pn_gamma, *pn_beta;
+  const float* me_hi[3]; const float* me_lo[3]; const float* me_b[3];
+  const float *nq_hi, *nq_lo, *nq_b;                 // next layer's cross in_proj [768,256] split (null = last layer)
+  float* trace;                                      // optional [nl,B*R,256]
+  int* zero_rows;                                    // optional [B*R]
+  int B, R, Nk, nl, ffn, ldvs, ncls, ldvc, has_cross_attn, m2f_tail;
+};
+int launch_decoder_chain(const ChainArgs& a, cudaStream_t st);
+size_t chain_scratch_floats(int B, int R, int ffn);
+
 int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,
                       int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 int launch_level_prep_tokens(const float* mem, long long bstride, const float* level_embed, const float* pos, float* x,
                              float* xp, int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_COUNT = 10 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_COUNT = 11 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);

@@ -309,6 +309,20 @@ class CrossHead2(nn.Module):
         self._lin(r.rel_cls_embed, self.rel_cls_embed)
         for i, layer in enumerate(rd.layers):
             self._layer(r.layers[i], layer)
+        # static operands of the tensor-core kernels (TF32 hi/lo weight splits): built once per weight version
+        lib = nat.load()
+        dev = params[0].device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._prepared = []
+        for sub, size_fn, prep_fn in ((m, lib.pn_m2f_prepared_bytes, lib.pn_m2f_prepare),
+                                      (r, lib.pn_rel_prepared_bytes, lib.pn_rel_prepare)):
+            need = size_fn(C.byref(sub))
+            if need == 0:
+                raise nat.NativeError("prepared-weights size query failed: " + lib.pn_last_error_string().decode())
+            buf = torch.empty(need, dtype=torch.uint8, device=dev)
+            nat.check(prep_fn(C.byref(sub), buf.data_ptr(), need, stream), "pn_*_prepare")
+            sub.prepared = buf.data_ptr()
+            self._prepared.append(buf)
         self._wkey, self._wstruct = key, w
         return w
 
