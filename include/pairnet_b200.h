@@ -90,8 +90,11 @@ PN_API int pn_get_option(int key);
                                  * operands split in the SM); 0 = exact-fp32 FFMA */
 #define PN_OPT_MASK_TC 9        /* default 1: mask einsums (attention-mask bits, final mask_pred) on the tcgen05 GEMM with
                                    token-major operands; 0 = FFMA kernels on NCHW / N-major operands */
-#define PN_OPT_FUSED_CHAIN 10    /* default 1: decoders whose weights carry a prepared blob (pn_*_prepare) run their query-side
-                                   layers as ONE cluster launch of the fused tcgen05 chain kernel (chain.cu); 0 = per-op kernels */
+#define PN_OPT_FUSED_CHAIN 10    /* Relation Fusion decoder with prepared weights (pn_rel_prepare): key side of all layers on the
+                                   tcgen05 GEMM, then  2 = always ONE cluster launch of the fused tcgen05 chain kernel (chain.cu:
+                                   6 layers + classifier);  1 (default) = that chain from 8 images per call (it runs 8 SMs per
+                                   image), below per-op kernels on all SMs with the cross attention on tcgen05 (fa_umma.cu);
+                                   0 = round-1 per-op kernels (warp-MMA linears, FFMA attention), prepared blob unused */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */
@@ -371,6 +374,9 @@ PN_API int pn_head_forward(const PnHeadWeights* w, const PnM2FInputs* in, const 
                     void* ws, size_t ws_bytes, pn_stream_t stream);
 /* number of kernels pn_head_forward enqueued on its last call on this thread */
 PN_API int pn_last_launch_count(void);
+/* profiling hook of the fused decoder-chain kernel: when set (device buffer of `capacity` u64), cluster 0 / rank 0 writes
+ * %globaltimer (ns) at kernel start and after every phase barrier.  NULL switches it off (default). */
+PN_API int pn_debug_chain_timing(unsigned long long* device_buf, int capacity);
 
 #ifdef __cplusplus
 }

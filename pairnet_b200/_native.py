@@ -100,6 +100,7 @@ SIGNATURES = {
     "pn_version": (i32, []),
     "pn_last_error_string": (C.c_char_p, []),
     "pn_last_launch_count": (i32, []),
+    "pn_debug_chain_timing": (i32, [vp, i32]),
     "pn_set_option": (i32, [i32, i32]),
     "pn_get_option": (i32, [i32]),
     "pn_device_info": (i32, [P(i32), P(i32), P(i32)]),

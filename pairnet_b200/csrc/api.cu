@@ -88,6 +88,7 @@ static int mlp3(const float* x, const PnMlp3& m, float* t1, float* t2, float* y,
 struct FaKV {
   const float *k_hi, *k_lo, *vt_hi, *vt_lo;
   int ldv;
+  int ldk = 0, k_col0 = 0, vt_img_rows = 0, vt_row0 = 0;  // strided views (0 = dense), see FaArgs
 };
 
 struct LayerScratch {
@@ -137,6 +138,7 @@ static int decoder_layer(const PnDecoderLayer& L, int ffn, float* x, float* xpos
       float* q_lo = s.qk + (size_t)M * D;
       PN_TRY(launch_split_tf32_scaled(s.qp, q_hi, q_lo, (size_t)M * D, ATTN_QSCALE, st));
       FaArgs a{q_hi, q_lo, fa->k_hi, fa->k_lo, fa->vt_hi, fa->vt_lo, fa->ldv, bits, words, rowany, s.att, B, Nq, Nk};
+      a.ldk = fa->ldk; a.k_col0 = fa->k_col0; a.vt_img_rows = fa->vt_img_rows; a.vt_row0 = fa->vt_row0;
       PN_TRY(launch_fa_umma(a, s.mha_ws, s.mha_ws_bytes, st));
     } else {
       MhaArgs a{s.qp, D, kproj, D, vproj, D, bits, words, rowany, s.att, B, Nq, Nk};
@@ -660,53 +662,37 @@ static void carve_rel(Workspace& ws, const PnRelWeights* w, PreparedRel& p) {
   p.bk = ws.take<float>((size_t)nl * D); p.bv = ws.take<float>((size_t)nl * D);
   p.cls_hi = ws.take<float>((size_t)w->num_rel_cls * D); p.cls_lo = ws.take<float>((size_t)w->num_rel_cls * D);
 }
-static bool rel_fused_ok(const PnRelWeights* w) {
-  return w->prepared && get_option(OPT_FUSED_CHAIN) && get_option(OPT_TENSOR_CORES) && w->num_layers <= CHAIN_MAX_LAYERS &&
+constexpr int CHAIN_AUTO_MIN_BATCH = 8;  // PN_OPT_FUSED_CHAIN = 1: cluster chain from this many images per call (measured)
+// tensor-core key side available: prepared blob + tcgen05 enabled
+static bool rel_prepared_ok(const PnRelWeights* w) {
+  return w->prepared && get_option(OPT_TENSOR_CORES) && get_option(OPT_FUSED_CHAIN) != 0;
+}
+static bool rel_chain_ok(const PnRelWeights* w, int B) {
+  const int opt = get_option(OPT_FUSED_CHAIN);
+  return rel_prepared_ok(w) && (opt >= 2 || (opt == 1 && B >= CHAIN_AUTO_MIN_BATCH)) && w->num_layers <= CHAIN_MAX_LAYERS &&
          w->ffn_dims % 1024 == 0 && w->num_rel_cls <= 128 && w->num_rel_cls % 4 == 0;
 }
 
-struct RelFusedBufs {
-  float *x, *xpos, *pk, *p_hi, *p_lo, *kc_hi, *kc_lo, *vtc_hi, *vtc_lo, *scratch;
+// key-side operands of ALL relation layers (pair features do not change across layers, pairnet_head.py:365-376)
+struct RelKeyBufs {
+  float *pk, *p_hi, *p_lo, *kc_hi, *kc_lo, *vtc_hi, *vtc_lo;
 };
-static void rel_take_fused(Workspace& ws, int B, int R, int K2, int nl, int ffn, RelFusedBufs& b) {
-  const size_t M = (size_t)B * R, Mk = (size_t)B * K2;
+static void rel_take_keys(Workspace& ws, int B, int K2, int nl, RelKeyBufs& b) {
+  const size_t Mk = (size_t)B * K2;
   const size_t ldvc = (size_t)round_up(K2, 4);
-  b.x = ws.take<float>(M * D); b.xpos = ws.take<float>(M * D);
   b.pk = ws.take<float>(Mk * D); b.p_hi = ws.take<float>(Mk * D); b.p_lo = ws.take<float>(Mk * D);
   b.kc_hi = ws.take<float>(Mk * nl * D); b.kc_lo = ws.take<float>(Mk * nl * D);
   b.vtc_hi = ws.take<float>((size_t)B * nl * D * ldvc); b.vtc_lo = ws.take<float>((size_t)B * nl * D * ldvc);
-  b.scratch = ws.take<float>(chain_scratch_floats(B, R, ffn));
 }
-// carve the chain kernel's scratch (layout of chain_scratch_floats)
-static void chain_carve(float* s, int B, int R, int ffn, ChainArgs& a) {
-  const size_t M = (size_t)B * R, MD = M * D;
-  const size_t ldvs = (size_t)round_up(R, 4);
-  a.x1 = s; s += MD; a.x1pos = s; s += MD; a.x2 = s; s += MD; a.pre = s; s += MD; a.att = s; s += MD;
-  a.h = s; s += M * ffn; a.parts = s; s += 8 * MD;
-  a.q_hi = s; s += MD; a.q_lo = s; s += MD; a.ks_hi = s; s += MD; a.ks_lo = s; s += MD;
-  a.vts_hi = s; s += (size_t)B * D * ldvs; a.vts_lo = s; s += (size_t)B * D * ldvs;
-  a.ldvs = (int)ldvs;
-}
-
-// Relation Fusion (pairnet_head.py:353-378) on the fused chain: 5 launches in front (key-side operands of all
-// layers on the tcgen05 GEMM), then ONE cluster launch for the six layers + the relation classifier.
-static int rel_forward_fused(const PnRelWeights* w, const float* pair_feat, float* rel_preds, float* rel_feat_out, int B,
-                             int K2, Workspace& ws, cudaStream_t st) {
-  const int R = w->num_rel_queries, nl = w->num_layers, ffn = w->ffn_dims;
-  PreparedRel P;
-  {
-    Workspace pw(const_cast<void*>(w->prepared), (size_t)1 << 60);
-    carve_rel(pw, w, P);
-  }
-  RelFusedBufs b;
-  rel_take_fused(ws, B, R, K2, nl, ffn, b);
-  PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "relation_fusion: workspace too small");
+// 4 launches on the tcgen05 GEMM: K [B*K2, nl*256] and V^T [B*nl*256, ldvc] of every layer, emitted as TF32 hi/lo pairs
+static int rel_key_side(const PnRelWeights* w, const PreparedRel& P, const float* pair_feat, const RelKeyBufs& b, int B,
+                        int K2, cudaStream_t st) {
+  const int nl = w->num_layers;
   const int Mk = B * K2, ldk = nl * D;
   const int ldvc = (int)round_up(K2, 4);
   PN_TRY(launch_add_rows(pair_feat, w->rel_query_embed2, b.pk, B, K2, st));
   PN_TRY(launch_split_tf32(pair_feat, b.p_hi, b.p_lo, (size_t)Mk * D, st));
-  // K of every layer: [Mk, nl*256] = (pair + key_pos) [Wk_0; ..; Wk_nl-1]^T, emitted split hi/lo (column chunks <= 1024)
-  {
+  {  // K = (pair + key_pos) [Wk_0; ..; Wk_nl-1]^T + bk   (column chunks <= 1024: bias staging limit of the GEMM)
     UmmaOperand o[4];
     int n = 0;
     for (int n0 = 0; n0 < ldk; n0 += 1024) {
@@ -719,8 +705,7 @@ static int rel_forward_fused(const PnRelWeights* w, const float* pair_feat, floa
       if (n == 4 || n0 + 1024 >= ldk) { PN_TRY(launch_umma_gemm(o, n, 3, st)); n = 0; }
     }
   }
-  // V^T of every layer, per image: [nl*256, K2] = [Wv_0; ..] pair_b^T + bv (weights as the A operand, row chunks <= 1024)
-  {
+  {  // V^T per image = [Wv_0; ..] pair_b^T + bv (weights as the A operand, per-row bias, row chunks <= 1024)
     UmmaOperand o[4];
     int n = 0;
     for (int bi = 0; bi < B; ++bi)
@@ -735,65 +720,94 @@ static int rel_forward_fused(const PnRelWeights* w, const float* pair_feat, floa
         if (n == 4 || last) { PN_TRY(launch_umma_gemm(o, n, 3, st)); n = 0; }
       }
   }
-  ChainArgs a{};
-  for (int l = 0; l < nl; ++l) chain_layer_fill(a.layers[l], w->layers[l], P.L[l]);
-  chain_carve(b.scratch, B, R, ffn, a);
-  a.x = b.x; a.xpos = b.xpos;
-  a.kc_hi = b.kc_hi; a.kc_lo = b.kc_lo; a.vtc_hi = b.vtc_hi; a.vtc_lo = b.vtc_lo;
-  a.init_feat = w->rel_query_feat; a.qpos = w->rel_query_embed;
-  a.cls_hi = P.cls_hi; a.cls_lo = P.cls_lo; a.cls_b = w->rel_cls_embed.b; a.cls_out = rel_preds;
-  a.B = B; a.R = R; a.Nk = K2; a.nl = nl; a.ffn = ffn; a.ncls = w->num_rel_cls; a.ldvc = ldvc; a.has_cross_attn = 1;
-  PN_TRY(launch_decoder_chain(a, st));
-  if (rel_feat_out) PN_TRY(copy_async(rel_feat_out, b.x, sizeof(float) * (size_t)B * R * D, st));
   return 0;
 }
 
-static void rel_take(Workspace& ws, int B, int R, int K2, int nl, int ffn, float** x, float** xpos, float** pk,
-                     float** Kall, float** Vall, LayerScratch& ls) {
+struct RelBufs {
+  float *x, *xpos, *pk, *Kall, *Vall, *chain_scratch;
+  RelKeyBufs keys;
+  LayerScratch ls;
+};
+// one carve-up for all three variants (per-op FFMA keys, per-op tensor-core keys, cluster chain): sized for the largest
+static void rel_take(Workspace& ws, int B, int R, int K2, int nl, int ffn, RelBufs& b) {
   const int M = B * R, Mk = B * K2;
-  *x = ws.take<float>((size_t)M * D);
-  *xpos = ws.take<float>((size_t)M * D);
-  *pk = ws.take<float>((size_t)Mk * D);
-  *Kall = ws.take<float>((size_t)nl * Mk * D);
-  *Vall = ws.take<float>((size_t)nl * Mk * D);
+  b.x = ws.take<float>((size_t)M * D);
+  b.xpos = ws.take<float>((size_t)M * D);
+  b.pk = ws.take<float>((size_t)Mk * D);
+  b.Kall = ws.take<float>((size_t)nl * Mk * D);
+  b.Vall = ws.take<float>((size_t)nl * Mk * D);
+  rel_take_keys(ws, B, K2, nl, b.keys);
+  b.chain_scratch = ws.take<float>(chain_scratch_floats(B, R, ffn));
   size_t mb = mha_workspace_bytes(B, R, K2);
   size_t mb2 = mha_workspace_bytes(B, R, R);
-  layer_scratch_take(ws, ls, M, ffn, mb > mb2 ? mb : mb2);
+  size_t mb3 = fa_workspace_bytes(B, R, K2);
+  mb = mb > mb2 ? mb : mb2;
+  layer_scratch_take(ws, b.ls, M, ffn, mb > mb3 ? mb : mb3);
 }
 
+// Relation Fusion decoder + relation classifier (pairnet_head.py:353-378).
+//   prepared weights + tensor cores: the key side of all layers runs on the tcgen05 GEMM (4 launches), then either
+//     * ONE cluster launch of the fused chain kernel (chain.cu) for the six layers + classifier  (PN_OPT_FUSED_CHAIN = 2,
+//       or = 1 with >= 8 images: the chain uses 8 SMs per image, so it wins once a batch fills the GPU), or
+//     * per-op kernels on all SMs with the cross attention on tcgen05 (fa_umma.cu) -- the fastest path at bs = 2;
+//   otherwise: exact-fp32 / warp-MMA per-op kernels as in round 1.
 static int rel_forward(const PnRelWeights* w, const float* pair_feat, float* rel_preds, float* rel_feat_out, int B,
                        int K2, Workspace& ws, cudaStream_t st) {
   PN_REQUIRE(w && pair_feat && rel_preds, PN_ERR_BAD_ARG, "relation_fusion: null pointer");
   const int R = w->num_rel_queries, nl = w->num_layers, ffn = w->ffn_dims;
   PN_REQUIRE(R > 0 && K2 > 0 && B > 0 && nl >= 1 && nl <= PN_MAX_LAYERS, PN_ERR_BAD_ARG, "relation_fusion: bad sizes");
-  if (rel_fused_ok(w)) return rel_forward_fused(w, pair_feat, rel_preds, rel_feat_out, B, K2, ws, st);
   const int M = B * R, Mk = B * K2;
-  float *x, *xpos, *pk, *Kall, *Vall;
-  LayerScratch ls;
-  rel_take(ws, B, R, K2, nl, ffn, &x, &xpos, &pk, &Kall, &Vall, ls);
+  RelBufs b;
+  rel_take(ws, B, R, K2, nl, ffn, b);
   PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "relation_fusion: workspace too small");
+  const bool prep = rel_prepared_ok(w);
+  PreparedRel P{};
+  if (prep) {
+    Workspace pw(const_cast<void*>(w->prepared), (size_t)1 << 60);
+    carve_rel(pw, w, P);
+    PN_TRY(rel_key_side(w, P, pair_feat, b.keys, B, K2, st));
+  }
+  const int ldvc = (int)round_up(K2, 4);
+  if (rel_chain_ok(w, B)) {
+    ChainArgs a{};
+    for (int l = 0; l < nl; ++l) chain_layer_fill(a.layers[l], w->layers[l], P.L[l]);
+    a.x = b.x; a.scratch = b.chain_scratch;
+    a.kc_hi = b.keys.kc_hi; a.kc_lo = b.keys.kc_lo; a.vtc_hi = b.keys.vtc_hi; a.vtc_lo = b.keys.vtc_lo;
+    a.init_feat = w->rel_query_feat; a.qpos = w->rel_query_embed;
+    a.cls_hi = P.cls_hi; a.cls_lo = P.cls_lo; a.cls_b = w->rel_cls_embed.b; a.cls_out = rel_preds;
+    a.B = B; a.R = R; a.Nk = K2; a.nl = nl; a.ffn = ffn; a.ncls = w->num_rel_cls; a.ldvc = ldvc; a.has_cross_attn = 1;
+    PN_TRY(launch_decoder_chain(a, st));
+    if (rel_feat_out) PN_TRY(copy_async(rel_feat_out, b.x, sizeof(float) * (size_t)M * D, st));
+    return 0;
+  }
 
-  PN_TRY(launch_bcast_rows(w->rel_query_feat, w->rel_query_embed, x, xpos, B, R, st));
-  PN_TRY(launch_add_rows(pair_feat, w->rel_query_embed2, pk, B, K2, st));
-  // K/V of every layer up front: pair_feat does not change across layers (pairnet_head.py:365-376)
-  for (int l0 = 0; l0 < nl; l0 += GEMM_MAX_PROBS / 2) {
-    GemmBatch g{};
-    int c = 0;
-    for (int l = l0; l < nl && c + 2 <= GEMM_MAX_PROBS; ++l) {
-      const PnMHA& a = w->layers[l].cross_attn;
-      g.p[c++] = make_linear(pk, D, a.in_proj_w + (size_t)D * D, a.in_proj_b + D, Kall + (size_t)l * Mk * D, D, Mk, D, D);
-      g.p[c++] = make_linear(pair_feat, D, a.in_proj_w + (size_t)2 * D * D, a.in_proj_b + 2 * D,
-                             Vall + (size_t)l * Mk * D, D, Mk, D, D);
+  PN_TRY(launch_bcast_rows(w->rel_query_feat, w->rel_query_embed, b.x, b.xpos, B, R, st));
+  if (!prep) {
+    PN_TRY(launch_add_rows(pair_feat, w->rel_query_embed2, b.pk, B, K2, st));
+    // K/V of every layer up front: pair_feat does not change across layers (pairnet_head.py:365-376)
+    for (int l0 = 0; l0 < nl; l0 += GEMM_MAX_PROBS / 2) {
+      GemmBatch g{};
+      int c = 0;
+      for (int l = l0; l < nl && c + 2 <= GEMM_MAX_PROBS; ++l) {
+        const PnMHA& a = w->layers[l].cross_attn;
+        g.p[c++] = make_linear(b.pk, D, a.in_proj_w + (size_t)D * D, a.in_proj_b + D, b.Kall + (size_t)l * Mk * D, D, Mk, D, D);
+        g.p[c++] = make_linear(pair_feat, D, a.in_proj_w + (size_t)2 * D * D, a.in_proj_b + 2 * D,
+                               b.Vall + (size_t)l * Mk * D, D, Mk, D, D);
+      }
+      g.count = c;
+      PN_TRY(launch_gemm(g, st));
     }
-    g.count = c;
-    PN_TRY(launch_gemm(g, st));
   }
   for (int l = 0; l < nl; ++l) {
-    PN_TRY(decoder_layer(w->layers[l], ffn, x, xpos, w->rel_query_embed, B, R, Kall + (size_t)l * Mk * D,
-                         Vall + (size_t)l * Mk * D, K2, nullptr, 0, nullptr, nullptr, nullptr, ls, st));
+    // tensor-core cross attention reads layer l's slice of the key-side operands in place
+    FaKV fa{b.keys.kc_hi, b.keys.kc_lo, b.keys.vtc_hi, b.keys.vtc_lo, ldvc};
+    fa.ldk = nl * D; fa.k_col0 = l * D; fa.vt_img_rows = nl * D; fa.vt_row0 = l * D;
+    PN_TRY(decoder_layer(w->layers[l], ffn, b.x, b.xpos, w->rel_query_embed, B, R, b.Kall + (size_t)l * Mk * D,
+                         b.Vall + (size_t)l * Mk * D, K2, nullptr, 0, nullptr, nullptr, nullptr, b.ls, st, nullptr, nullptr,
+                         prep ? &fa : nullptr));
   }
-  PN_TRY(linear1(x, D, w->rel_cls_embed, rel_preds, w->num_rel_cls, M, w->num_rel_cls, D, 0, st));
-  if (rel_feat_out) PN_TRY(copy_async(rel_feat_out, x, sizeof(float) * M * D, st));
+  PN_TRY(linear1(b.x, D, w->rel_cls_embed, rel_preds, w->num_rel_cls, M, w->num_rel_cls, D, 0, st));
+  if (rel_feat_out) PN_TRY(copy_async(rel_feat_out, b.x, sizeof(float) * M * D, st));
   return 0;
 }
 
@@ -815,6 +829,10 @@ int pn_set_option(int key, int value) {
 int pn_get_option(int key) { return get_option(key); }
 const char* pn_last_error_string(void) { return g_err; }
 int pn_last_launch_count(void) { return g_launches; }
+int pn_debug_chain_timing(unsigned long long* device_buf, int capacity) {
+  chain_set_timing(device_buf, capacity);
+  return 0;
+}
 
 int pn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -1028,13 +1046,9 @@ int pn_topk_pairs(const float* importance, int64_t* topk_idx, int64_t* sub_pos, 
 
 size_t pn_relation_fusion_workspace_bytes(int B, int R, int K2, int ffn_dims) {
   Workspace ws(nullptr, 0);
-  float *a, *b, *c, *d, *e;
-  LayerScratch ls;
-  rel_take(ws, B, R, K2, PN_MAX_LAYERS, ffn_dims, &a, &b, &c, &d, &e, ls);
-  Workspace wf(nullptr, 0);
-  RelFusedBufs fb;
-  rel_take_fused(wf, B, R, K2, CHAIN_MAX_LAYERS, ffn_dims, fb);
-  return (ws.off > wf.off ? ws.off : wf.off) + 1024;
+  RelBufs rb;
+  rel_take(ws, B, R, K2, PN_MAX_LAYERS, ffn_dims, rb);
+  return ws.off + 1024;
 }
 
 size_t pn_m2f_prepared_bytes(const PnM2FWeights* w) {

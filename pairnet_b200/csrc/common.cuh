@@ -155,6 +155,9 @@ struct FaArgs {
   const int* rowany;
   float* out;                                // [B,Nq,256]
   int B, Nq, Nk;
+  // optional strided views (0 = dense defaults): K rows have leading dimension ldk (columns k_col0 .. k_col0+255 are
+  // used); V^T of image b starts at row b * vt_img_rows + vt_row0
+  int ldk, k_col0, vt_img_rows, vt_row0;
 };
 size_t fa_workspace_bytes(int B, int Nq, int Nk);
 int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -172,26 +175,29 @@ struct ChainLayer {  // hi/lo TF32 splits of one layer's weights (row-major, tor
 };
 struct ChainArgs {
   ChainLayer layers[CHAIN_MAX_LAYERS];
-  float *x, *xpos;                                   // [B*R,256] in/out (written from init_feat when given)
-  float *pre, *x1, *x1pos, *x2, *att, *h, *parts;    // scratch: [B*R,256] x5, [B*R,ffn], [8][B*R,256]
-  float *q_hi, *q_lo, *ks_hi, *ks_lo;                // [B*R,256]
-  float *vts_hi, *vts_lo;                            // [B*256, ldvs]
+  float* x;                                          // [B*R,256] fp32 layer input / output (written from init_feat when given)
+  float* scratch;                                    // chain_scratch_floats(B, R, ffn) floats
+  // activations exchanged with other kernels as TF32 hi/lo pairs (null = internal scratch):
+  float *xpos_hi, *xpos_lo;                          //   x + query_pos   [B*R,256]  (in when init_feat is null; out)
+  float *att_hi, *att_lo;                            //   cross-attention output [B*R,256]  (in when !has_cross_attn)
+  float *q_hi, *q_lo;                                //   scaled query projection of the NEXT layer's cross attention (out)
   const float *kc_hi, *kc_lo;                        // cross keys of all layers [B*Nk, nl*256]   (has_cross_attn)
   const float *vtc_hi, *vtc_lo;                      // cross V^T [B*nl*256, ldvc]
   const float *init_feat, *qpos;                     // [R,256]
   const float *cls_hi, *cls_lo, *cls_b;              // final classifier [ncls,256] (cls_out null = none)
   float* cls_out;
-  // Mask2Former tail: xn = post_norm(x), e = mask_embed(xn) split hi/lo, q of the next layer's cross-attention
-  float *xn, *e1, *e2, *e_hi, *e_lo;
+  // Mask2Former tail: xn = post_norm(x) (fp32 out), e = mask_embed(xn) split hi/lo, q of the next layer's cross-attention
+  float *xn, *e_hi, *e_lo;
   const float *pn_gamma, *pn_beta;
   const float* me_hi[3]; const float* me_lo[3]; const float* me_b[3];
   const float *nq_hi, *nq_lo, *nq_b;                 // next layer's cross in_proj [768,256] split (null = last layer)
   float* trace;                                      // optional [nl,B*R,256]
   int* zero_rows;                                    // optional [B*R]
-  int B, R, Nk, nl, ffn, ldvs, ncls, ldvc, has_cross_attn, m2f_tail;
+  int B, R, Nk, nl, ffn, ncls, ldvc, has_cross_attn, m2f_tail;
 };
 int launch_decoder_chain(const ChainArgs& a, cudaStream_t st);
 size_t chain_scratch_floats(int B, int R, int ffn);
+void chain_set_timing(unsigned long long* buf, int cap);
 
 int launch_sine_posenc(float* pos, int h, int w, cudaStream_t st);
 int launch_level_prep(const float* mem, const float* level_embed, const float* pos, float* x, float* xp,

@@ -41,6 +41,7 @@ struct Params {
   float* opart;    // [S,B,Nq,256]
   float2* ml;      // [S,B,NH,Nq]
   int B, Nq, Nk, splits, tiles_per_split;
+  int k_col0, vt_img_rows, vt_row0;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_constant__ Params prm) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
   uint64_t* o_full = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int split = blockIdx.x, h = blockIdx.y;
   const int qtiles = (prm.Nq + TQ - 1) / TQ;
   const int b = blockIdx.z / qtiles, qt = blockIdx.z % qtiles;
@@ -83,42 +84,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = uniform_u32(*tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues the TMA (see elect_one)
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * TILE16K);
       tma_load_2d(q_hi_s, &prm.q_hi, q_full, h * HD, b * prm.Nq + qt * TQ);
       tma_load_2d(q_lo_s, &prm.q_lo, q_full, h * HD, b * prm.Nq + qt * TQ);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t* st = stage0 + (size_t)s * STAGE_BYTES;
-        const int key0 = (tile0 + t) * TKEYS;
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      uint8_t* st = stage0 + (size_t)s * STAGE_BYTES;
+      const int key0 = (tile0 + t) * TKEYS;
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[s], STAGE_BYTES);
-        tma_load_2d(st, &prm.k_hi, &kv_full[s], h * HD, b * prm.Nk + key0);
-        tma_load_2d(st + TILE16K, &prm.k_lo, &kv_full[s], h * HD, b * prm.Nk + key0);
+        tma_load_2d(st, &prm.k_hi, &kv_full[s], prm.k_col0 + h * HD, b * prm.Nk + key0);
+        tma_load_2d(st + TILE16K, &prm.k_lo, &kv_full[s], prm.k_col0 + h * HD, b * prm.Nk + key0);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          tma_load_2d(st + 2 * TILE16K + a * VT_ATOM, &prm.vt_hi, &kv_full[s], key0 + a * 32, (b * NH + h) * HD);
-          tma_load_2d(st + 3 * TILE16K + a * VT_ATOM, &prm.vt_lo, &kv_full[s], key0 + a * 32, (b * NH + h) * HD);
+          tma_load_2d(st + 2 * TILE16K + a * VT_ATOM, &prm.vt_hi, &kv_full[s], key0 + a * 32, b * prm.vt_img_rows + prm.vt_row0 + h * HD);
+          tma_load_2d(st + 3 * TILE16K + a * VT_ATOM, &prm.vt_lo, &kv_full[s], key0 + a * 32, b * prm.vt_img_rows + prm.vt_row0 + h * HD);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(TKEYS);  // M=128, N=128 keys
-      const uint32_t idesc_o = make_idesc(HD);     // M=128, N=32 dims
-      mbar_wait(q_full, 0);
-      const uint64_t dq_hi = make_smem_desc(smem_u32(q_hi_s)), dq_lo = make_smem_desc(smem_u32(q_lo_s));
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&kv_full[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(stage0 + (size_t)s * STAGE_BYTES);
-        const uint64_t dk_hi = make_smem_desc(st), dk_lo = make_smem_desc(st + TILE16K);
+    const uint32_t idesc_s = make_idesc(TKEYS);  // M=128, N=128 keys
+    const uint32_t idesc_o = make_idesc(HD);     // M=128, N=32 dims
+    mbar_wait(q_full, 0);
+    const uint64_t dq_hi = make_smem_desc(smem_u32(q_hi_s)), dq_lo = make_smem_desc(smem_u32(q_lo_s));
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      mbar_wait(&kv_full[s], ph);
+      tc_fence_after();
+      const uint32_t st = smem_u32(stage0 + (size_t)s * STAGE_BYTES);
+      const uint64_t dk_hi = make_smem_desc(st), dk_lo = make_smem_desc(st + TILE16K);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / UMMA_K; ++k) {
           const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
@@ -127,8 +133,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
           umma_tf32(tmem + TM_S, dq_hi + koff, dk_hi + koff, idesc_s, 1u);
         }
         umma_commit(s_full);
-        mbar_wait(p_ready, t & 1);  // softmax warps have consumed S and written P (hi, lo) to TMEM
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(p_ready, t & 1);  // softmax warps have consumed S and written P (hi, lo) to TMEM
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
@@ -145,6 +154,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
       }
+      __syncwarp();
     }
   } else {
     // ===== softmax / accumulate: one query row per thread
@@ -269,10 +279,15 @@ int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) 
   Params prm{};
   PN_TRY(umma::make_tmap_2d(&prm.q_hi, a.q_hi, (long long)a.B * a.Nq, D, D, 32, TQ));
   PN_TRY(umma::make_tmap_2d(&prm.q_lo, a.q_lo, (long long)a.B * a.Nq, D, D, 32, TQ));
-  PN_TRY(umma::make_tmap_2d(&prm.k_hi, a.k_hi, (long long)a.B * a.Nk, D, D, 32, TKEYS));
-  PN_TRY(umma::make_tmap_2d(&prm.k_lo, a.k_lo, (long long)a.B * a.Nk, D, D, 32, TKEYS));
-  PN_TRY(umma::make_tmap_2d(&prm.vt_hi, a.vt_hi, (long long)a.B * D, a.Nk, a.ldv, 32, HD));
-  PN_TRY(umma::make_tmap_2d(&prm.vt_lo, a.vt_lo, (long long)a.B * D, a.Nk, a.ldv, 32, HD));
+  const int ldk = a.ldk > 0 ? a.ldk : D;
+  const int vt_img_rows = a.vt_img_rows > 0 ? a.vt_img_rows : D;
+  PN_REQUIRE(ldk % 4 == 0 && a.k_col0 % 32 == 0 && a.k_col0 + D <= ldk && a.vt_row0 + D <= vt_img_rows, PN_ERR_BAD_ARG,
+             "fa: bad K / V^T view");
+  PN_TRY(umma::make_tmap_2d(&prm.k_hi, a.k_hi, (long long)a.B * a.Nk, ldk, ldk, 32, TKEYS));
+  PN_TRY(umma::make_tmap_2d(&prm.k_lo, a.k_lo, (long long)a.B * a.Nk, ldk, ldk, 32, TKEYS));
+  PN_TRY(umma::make_tmap_2d(&prm.vt_hi, a.vt_hi, (long long)a.B * vt_img_rows, a.Nk, a.ldv, 32, HD));
+  PN_TRY(umma::make_tmap_2d(&prm.vt_lo, a.vt_lo, (long long)a.B * vt_img_rows, a.Nk, a.ldv, 32, HD));
+  prm.k_col0 = a.k_col0; prm.vt_img_rows = vt_img_rows; prm.vt_row0 = a.vt_row0;
   prm.mask_bits = a.mask_bits; prm.mask_words = a.mask_words; prm.rowany = a.rowany;
   prm.out = a.out; prm.B = a.B; prm.Nq = a.Nq; prm.Nk = a.Nk;
   const int qtiles = cdiv(a.Nq, TQ);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_umma_kernel(const __grid_
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                                      // [2] epilogue -> MMA
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -104,46 +104,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_umma_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_base_slot);
   const int num_kb = prm.K / BK;
   // rows of O actually needed by one n-tile, in 128-row boxes
   const int oboxes = (prm.bn + 127) / 128;
   const uint32_t stage_tx = (uint32_t)(TILE16K + oboxes * TILE16K);
 
   if (warp == 0) {
-    // ===== TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(prm, t);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          uint8_t* st = smem + (size_t)s * C::STAGE_BYTES;
+    // ===== TMA producer (warp-uniform loop, one elected lane issues)
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(prm, t);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + (size_t)s * C::STAGE_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], stage_tx);
           tma_load_3d(st + C::OFF_S_HI, &prm.s_map, &full_bar[s], kb * BK, tc.m0, tc.b);
           for (int h = 0; h < oboxes; ++h)
             tma_load_3d(st + C::OFF_O_HI + h * TILE16K, &prm.o_map, &full_bar[s], kb * BK, tc.n0 + h * 128, tc.b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(prm.bn);
-      uint32_t it = 0, tile_it = 0;
-      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
-        const uint32_t acc = tile_it & 1;
-        mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues)
+    const uint32_t idesc = make_idesc(prm.bn);
+    uint32_t it = 0, tile_it = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
+      const uint32_t acc = tile_it & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BNMAX;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&split_bar[s], (it / STAGES) & 1);  // hi/lo tiles of this k-block are in smem
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BNMAX;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&split_bar[s], (it / STAGES) & 1);  // hi/lo tiles of this k-block are in smem
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(st + C::OFF_S_HI), a_lo = make_smem_desc(st + C::OFF_S_LO);
-          const uint64_t b_hi = make_smem_desc(st + C::OFF_O_HI), b_lo = make_smem_desc(st + C::OFF_O_LO);
+        const uint32_t st = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(st + C::OFF_S_HI), a_lo = make_smem_desc(st + C::OFF_S_LO);
+        const uint64_t b_hi = make_smem_desc(st + C::OFF_O_HI), b_lo = make_smem_desc(st + C::OFF_O_LO);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
@@ -154,8 +155,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_umma_kernel(const __grid_
           }
           umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+      __syncwarp();
     }
   } else if (warp < 2 + NUM_EPI_WARPS) {
     // ===== epilogue: TMEM lane quadrant = warp % 4; one output row per thread

@@ -108,7 +108,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_free_bar + ASETS);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const bool is_epi = warp >= 2 && warp < 2 + NUM_EPI_WARPS;
   if (is_epi) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
     for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += 32 * NUM_EPI_WARPS) {
@@ -144,23 +144,23 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_base_slot);
 
   if (warp == 0) {
-    // ===== TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;  // global k-block counter -> smem ring position
-      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord<BN>(prm, t);
-        const Problem& P = prm.p[tc.p];
-        const int num_kb = P.K / BK;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-          const uint32_t bytes = A_RAW ? (uint32_t)STAGE_BYTES
-                                       : ((prm.passes == 3) ? (uint32_t)STAGE_BYTES : (uint32_t)STAGE_BYTES / 2);
+    // ===== TMA producer: the whole warp walks the loop (warp-uniform control flow), one elected lane issues
+    uint32_t it = 0;  // global k-block counter -> smem ring position
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord<BN>(prm, t);
+      const Problem& P = prm.p[tc.p];
+      const int num_kb = P.K / BK;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        const uint32_t bytes = A_RAW ? (uint32_t)STAGE_BYTES
+                                     : ((prm.passes == 3) ? (uint32_t)STAGE_BYTES : (uint32_t)STAGE_BYTES / 2);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], bytes);
           // B tiles are loaded as BN/128 boxes of 128 rows (the tensor-map box is 32 x 128)
           tma_load_2d(st + OFF_A_HI, &P.a_hi, &full_bar[s], kb * BK, tc.m0);  // A_RAW: a_hi holds the raw A map
@@ -174,31 +174,32 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
               tma_load_2d(st + OFF_B_LO + h * A_TILE_BYTES, &P.b_lo, &full_bar[s], kb * BK, tc.n0 + h * 128);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BN);
-      uint32_t it = 0, tile_it = 0;
-      for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
-        const TileCoord tc = tile_coord<BN>(prm, t);
-        const int num_kb = prm.p[tc.p].K / BK;
-        const uint32_t acc = tile_it & 1;
-        mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t b_hi = make_smem_desc(st + OFF_B_HI), b_lo = make_smem_desc(st + OFF_B_LO);
-          if (A_RAW) {
-            const uint32_t set = it % ASETS;
-            mbar_wait(&a_ready_bar[set], (it / ASETS) & 1);  // splitter has parked hi/lo of this k-block in TMEM
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi_t = tmem_base + TM_A + set * 64, a_lo_t = a_hi_t + 32;
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
+    const uint32_t idesc = make_idesc(BN);
+    uint32_t it = 0, tile_it = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
+      const TileCoord tc = tile_coord<BN>(prm, t);
+      const int num_kb = prm.p[tc.p].K / BK;
+      const uint32_t acc = tile_it & 1;
+      mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t b_hi = make_smem_desc(st + OFF_B_HI), b_lo = make_smem_desc(st + OFF_B_LO);
+        if (A_RAW) {
+          const uint32_t set = it % ASETS;
+          mbar_wait(&a_ready_bar[set], (it / ASETS) & 1);  // splitter has parked hi/lo of this k-block in TMEM
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi_t = tmem_base + TM_A + set * 64, a_lo_t = a_hi_t + 32;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
@@ -209,9 +210,11 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
             }
             umma_commit(&empty_bar[s]);      // B tiles of this stage are free once these MMAs complete
             umma_commit(&a_free_bar[set]);   // ... and so is the TMEM A set
-          } else {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t a_hi = make_smem_desc(st + OFF_A_HI), a_lo = make_smem_desc(st + OFF_A_LO);
+          }
+        } else {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t a_hi = make_smem_desc(st + OFF_A_HI), a_lo = make_smem_desc(st + OFF_A_LO);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance inside the 128 B swizzle row
@@ -227,8 +230,10 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
             umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+      __syncwarp();
     }
   } else if (is_epi) {
     // ===== epilogue: TMEM lane quadrant (warp % 4), column slice ((warp - 2) / 4)

@@ -12,6 +12,24 @@ constexpr int UMMA_K = 8;  // kind::tf32: 32 bytes of K per instruction
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a CONVERGED warp.  Issuing TMA / tcgen05.mma under `if (elect_one())` inside warp-uniform
+// control flow keeps their operands in uniform registers; under `if (lane == 0)` every instruction is wrapped in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY uniformisation loop (~100 cycles per MMA, measured: the issue loop, not the
+// tensor pipe, bounded the k-block time).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp-uniform copy of a value (the compiler treats shuffle results as uniform)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -1,7 +1,10 @@
-"""GPU (-m gpu): the fused decoder-chain kernel (pairnet_b200/csrc/chain.cu) through the C-ABI stage entry point
-``pn_relation_fusion_forward``: six BaseTransformerLayers + the relation classifier in one cluster launch, against
- (a) the CPU oracle's relation decoder evaluated in float64 on the same pair features (pairnet_head.py:353-378),
- (b) the per-op kernel path (PN_OPT_FUSED_CHAIN = 0) of the same library."""
+"""GPU (-m gpu): the Relation Fusion decoder through the C-ABI stage entry point ``pn_relation_fusion_forward`` in its
+three variants (PN_OPT_FUSED_CHAIN):
+  2 = the fused decoder-chain kernel (pairnet_b200/csrc/chain.cu): six BaseTransformerLayers + the relation classifier
+      in ONE tcgen05 cluster launch (+ 4 key-side GEMM launches),
+  1 = auto: chain from 8 images per call, below that per-op kernels with the key side and the cross attention on tcgen05,
+  0 = round-1 per-op kernels (warp-MMA linears, FFMA attention),
+against the CPU oracle's relation decoder evaluated in float64 on the same pair features (pairnet_head.py:353-378)."""
 import ctypes as C
 
 import pytest
@@ -43,7 +46,7 @@ def _oracle_relation_fusion(o, pair_feat):
         return x.transpose(0, 1), o.rel_cls_embed(x.transpose(0, 1))
 
 
-def _run_stage(p, pair_feat, fused):
+def _run_stage(p, pair_feat, mode):
     from pairnet_b200 import _native as nat
     lib = nat.load()
     w = p.native_weights()
@@ -54,7 +57,7 @@ def _run_stage(p, pair_feat, fused):
     rel = torch.zeros((B, R, p.num_relations), device="cuda")
     feat = torch.zeros((B, R, 256), device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    lib.pn_set_option(nat.PN_OPT_FUSED_CHAIN, int(fused))
+    lib.pn_set_option(nat.PN_OPT_FUSED_CHAIN, int(mode))
     try:
         nat.check(lib.pn_relation_fusion_forward(C.byref(w.rel), pair_feat.data_ptr(), rel.data_ptr(), feat.data_ptr(), B,
                                                  K2, ws.data_ptr(), need, st), "pn_relation_fusion_forward")
@@ -65,28 +68,30 @@ def _run_stage(p, pair_feat, fused):
     return rel, feat, launches
 
 
-@pytest.mark.parametrize("N,R,B", [(100, 100, 1), (100, 100, 2), (50, 30, 3), (200, 200, 1), (100, 100, 5)])
-def test_relation_fusion_fused_chain(N, R, B):
+@pytest.mark.parametrize("N,R,B", [(100, 100, 1), (100, 100, 2), (50, 30, 3), (200, 200, 1), (100, 100, 5), (100, 100, 9)])
+def test_relation_fusion_variants(N, R, B):
     o, p = _build(N, R)
     g = torch.Generator().manual_seed(1234 + R + B)
     pair = torch.randn((B, 2 * R, 256), generator=g)
     ref_feat, ref_rel = _oracle_relation_fusion(o, pair)
-    rel_f, feat_f, n_f = _run_stage(p, pair.cuda(), fused=True)
-    rel_u, feat_u, n_u = _run_stage(p, pair.cuda(), fused=False)
-    # the judge's bar for this stage: <= 12 launches for the whole Relation Fusion decoder (per-op path: ~105)
-    assert n_f <= 12, n_f
+    rel_c, feat_c, n_c = _run_stage(p, pair.cuda(), 2)
+    rel_a, feat_a, n_a = _run_stage(p, pair.cuda(), 1)
+    rel_u, feat_u, n_u = _run_stage(p, pair.cuda(), 0)
+    # the whole Relation Fusion decoder in <= 12 launches on the chain (per-op paths: ~85-95)
+    assert n_c <= 12, n_c
     assert n_u > 50, n_u
-    assert torch.isfinite(rel_f).all() and torch.isfinite(feat_f).all()
-    assert rel_err(feat_f, ref_feat) < 2e-5, "fused rel_feat vs float64 oracle"
-    assert rel_err(rel_f, ref_rel) < 2e-5, "fused rel logits vs float64 oracle"
-    assert rel_err(rel_u, ref_rel) < 2e-5, "per-op rel logits vs float64 oracle"
-    assert rel_err(rel_f, rel_u) < 2e-5
+    assert (n_a <= 12) == (B >= 8), (n_a, B)  # auto mode takes the chain from 8 images
+    for name, rel, feat in (("chain", rel_c, feat_c), ("auto", rel_a, feat_a), ("per-op", rel_u, feat_u)):
+        assert torch.isfinite(rel).all() and torch.isfinite(feat).all(), name
+        assert rel_err(feat, ref_feat) < 2e-5, f"{name}: rel_feat vs float64 oracle"
+        assert rel_err(rel, ref_rel) < 2e-5, f"{name}: rel logits vs float64 oracle"
 
 
-def test_relation_fusion_fused_chain_is_deterministic():
+def test_relation_fusion_is_deterministic():
     o, p = _build(100, 100)
     pair = torch.randn((2, 200, 256), generator=torch.Generator().manual_seed(5)).cuda()
-    a, fa, _ = _run_stage(p, pair, fused=True)
-    for _ in range(3):
-        b, fb, _ = _run_stage(p, pair, fused=True)
-        assert torch.equal(a, b) and torch.equal(fa, fb)
+    for mode in (2, 1):
+        a, fa, _ = _run_stage(p, pair, mode)
+        for _ in range(3):
+            b, fb, _ = _run_stage(p, pair, mode)
+            assert torch.equal(a, b) and torch.equal(fa, fb)
