@@ -88,6 +88,11 @@ class OCrossHead2(nn.Module):
         self.sub_query_update = _mlp3(d, d, d)
         self.obj_query_update = _mlp3(d, d, d)
         self.rel_cls_embed = nn.Linear(d, hp.num_relations)
+        # mmdet 2.25.1 SeesawLoss (rel_cls_loss, configs/mask2former/pairnet.py:153-158) registers the persistent buffer
+        # ``cum_samples`` [num_classes + 1]: part of every reference checkpoint.  Registered LAST so that the synthetic
+        # fixture weights (drawn in state_dict order, oracle/weights.py) of all other tensors are unchanged.
+        self.rel_cls_loss = nn.Module()
+        self.rel_cls_loss.register_buffer("cum_samples", torch.zeros(hp.num_relations + 1))
         self.n_heads = hp.num_heads
         self.num_obj_query = hp.num_obj_query
         self.num_rel_query = hp.num_rel_query

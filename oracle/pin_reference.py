@@ -39,7 +39,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 REF_CASES = [  # (tag, B, (H4,W4) of mask_feature, seed, N obj queries, R rel queries)
     ("b2_32x48", 2, (32, 48), 21, 100, 100),
     ("b1_40x56", 1, (40, 56), 22, 100, 100),
-    ("b3_24x40_n40_r24", 3, (24, 40), 23, 40, 24),
+    ("b3_24x40_n48_r32", 3, (24, 40), 23, 48, 32),   # spread pair rows (20-25 distinct subjects of 32)
     ("b1_32x32_n200_r200", 1, (32, 32), 24, 200, 200),   # BASELINE config 4's query count
 ]
 
@@ -179,9 +179,15 @@ def install_shims():
         def forward(self, feats):
             return feats
 
-    class _Loss:
+    class _Loss(nn.Module):
+        """loss builders are never called by the forward; mmdet's SeesawLoss contributes the persistent buffer
+        ``cum_samples`` [num_classes + 1] to the module tree (and so to every reference checkpoint)."""
+
         def __init__(self, cfg):
+            super().__init__()
             self.use_sigmoid = cfg.get("use_sigmoid", False)
+            if cfg.get("type") == "SeesawLoss":
+                self.register_buffer("cum_samples", torch.zeros(cfg.get("num_classes", 1203) + 1))
 
     def build_transformer_layer_sequence(cfg):
         """mmdet ``DetrTransformerDecoder`` container: ``layers`` (deep copies of one layer cfg), ``post_norm``,
@@ -261,7 +267,7 @@ def reference_head_cfg(num_obj_query=100, num_rel_query=100):
         positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True),
         loss_cls=dict(type="CrossEntropyLoss", use_sigmoid=False, class_weight=[1.0] * 133 + [0.1]),
         loss_mask=dict(type="CrossEntropyLoss", use_sigmoid=True), loss_dice=dict(type="DiceLoss"),
-        rel_cls_loss=dict(type="SeesawLoss"), subobj_cls_loss=dict(type="CrossEntropyLoss"),
+        rel_cls_loss=dict(type="SeesawLoss", num_classes=56), subobj_cls_loss=dict(type="CrossEntropyLoss"),
         importance_match_loss=dict(type="BCEWithLogitsLoss"), train_cfg=None, test_cfg=dict(max_per_img=100))
 
 

@@ -21,6 +21,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { ++g_launches; }
+int sm_count() {
+  static int cached[PN_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
 int check_launch(const char* what) {
   ++g_launches;
   cudaError_t e = cudaGetLastError();
@@ -36,12 +46,13 @@ int check_launch(const char* what) {
 // become parallel branches.  OPT_OVERLAP = 0 keeps everything on the caller's stream.
 struct Side {
   cudaStream_t s2 = nullptr;
-  cudaEvent_t ev[96];
+  cudaEvent_t ev[256];  // ring: an event is re-recorded only long after the wait on its previous record was enqueued (~30 per forward)
   int next = 0;
   bool ok = false;
 };
 static Side* get_side() {
-  static thread_local Side side;
+  static thread_local Side sides[PN_MAX_DEVICES];  // streams / events belong to the device that was current at creation
+  Side& side = sides[current_device()];
   if (!side.ok) {
     if (cudaStreamCreateWithFlags(&side.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (auto& e : side.ev)
@@ -52,7 +63,7 @@ static Side* get_side() {
 }
 static cudaEvent_t side_record(Side* sd, cudaStream_t on) {
   cudaEvent_t e = sd->ev[sd->next];
-  sd->next = (sd->next + 1) % 96;
+  sd->next = (sd->next + 1) % 256;
   cudaEventRecord(e, on);
   return e;
 }
@@ -612,13 +623,7 @@ static int ppn_forward(const float* query, const float* query_obj, const PnMlp3*
     int cb = (int)(PPN_L2_CHUNK_BYTES / img_bytes);
     // the top-k kernel runs one CTA per image: never hand it less than one wave of SMs (N = 400: 75 images fit the L2
     // budget, which left half of the 148 SMs idle), even if part of the chunk then spills to HBM
-    static int num_sms = 0;
-    if (num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = sm_count();
     cb = cb < num_sms ? num_sms : cb;
     for (int b0 = 0; b0 < B; b0 += cb) {
       const int nb = B - b0 < cb ? B - b0 : cb;

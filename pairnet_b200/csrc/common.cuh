@@ -32,6 +32,14 @@ int check_launch(const char* what);  // cudaGetLastError -> 0 / cudaError_t, rec
   } while (0)
 
 static inline cudaStream_t as_stream(pn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+// per-DEVICE caches (a process may drive several GPUs from several threads): SM count, and "function attributes set" flags
+constexpr int PN_MAX_DEVICES = 64;
+static inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < PN_MAX_DEVICES) ? dev : 0;
+}
+int sm_count();  // SMs of the current device (api.cu)
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 

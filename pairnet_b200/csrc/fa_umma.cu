@@ -295,13 +295,7 @@ int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) 
   const int total_tiles = cdiv(a.Nk, TKEYS);
   // one CTA per SM (TMEM: 512 columns; smem: 160 KB): keep the grid within ONE wave -- B*8*qtiles*splits <= #SMs --
   // a second, nearly empty wave doubles the kernel time (measured: 160 CTAs 103 us -> 144 CTAs 56 us at hw = 16 700)
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_count();
   int want = num_sms / base;
   want = want < 1 ? 1 : (want > 64 ? 64 : want);
   want = want > total_tiles ? total_tiles : want;
@@ -313,7 +307,8 @@ int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) 
     prm.opart = reinterpret_cast<float*>(ws);
     prm.ml = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) + o);
   }
-  static bool attr_set = false;
+  static bool attr_done[PN_MAX_DEVICES] = {false};  // the attribute is per device
+  bool& attr_set = attr_done[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fa_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     PN_REQUIRE(e == cudaSuccess, (int)e, "fa: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

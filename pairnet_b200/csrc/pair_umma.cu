@@ -286,7 +286,8 @@ int launch_pair_matrix_tc(const float* S, const float* O, float* C, int B, int N
   const long long tiles = (long long)B * prm.mtiles * prm.ntiles;
   PN_REQUIRE(tiles < (1ll << 31), PN_ERR_UNSUPPORTED, "pair matrix: too many tiles");
   prm.total_tiles = (int)tiles;
-  static bool attr_set = false;
+  static bool attr_done[PN_MAX_DEVICES] = {false};  // the attribute is per device
+  bool& attr_set = attr_done[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pair_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg<128>::SMEM_BYTES);
@@ -296,13 +297,7 @@ int launch_pair_matrix_tc(const float* S, const float* O, float* C, int B, int N
     PN_REQUIRE(e == cudaSuccess, (int)e, "pair matrix: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_count();
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
   if (prm.bn <= 128)
     pair_umma_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st>>>(prm);

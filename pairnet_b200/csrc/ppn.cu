@@ -193,7 +193,8 @@ static int conv_tiny_impl(const float* x, const PnConvTiny* cv, float* y, int B,
   conv1_kernel<C><<<g1, 256, 0, st>>>(x, cv->w[0], cv->b[0], a1, N);
   PN_TRY(check_launch("conv1_kernel"));
   const size_t smem2 = (size_t)(C2_CI * 49 * C + C2_CI * 14 * 24) * sizeof(float);
-  static bool attr_set = false;
+  static bool attr_done[PN_MAX_DEVICES] = {false};  // the attribute is per device
+  bool& attr_set = attr_done[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     PN_REQUIRE(e == cudaSuccess, (int)e, "conv2: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

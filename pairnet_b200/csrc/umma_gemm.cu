@@ -537,7 +537,8 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     maxM = o.M > maxM ? o.M : maxM;
     maxN = o.N > maxN ? o.N : maxN;
   }
-  static bool attr_set = false;
+  static bool attr_done[PN_MAX_DEVICES] = {false};  // the attribute is per device
+  bool& attr_set = attr_done[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg<128>::SMEM_BYTES);
@@ -564,13 +565,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   prm.count = count;
   prm.total_tiles = 0;
   for (int i = 0; i < count; ++i) prm.total_tiles += cdiv(ops[i].M, BM) * cdiv(ops[i].N, BN);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_count();
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
   if (raw && get_option(OPT_UMMA_EPI8))
     umma_gemm_kernel<128, 8, true><<<grid, 64 + 32 * 8 + 128, RAW_SMEM_BYTES, st>>>(prm);

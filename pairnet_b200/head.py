@@ -95,6 +95,21 @@ class CrossHead2(nn.Module):
         self.num_heads = transformer_decoder.transformerlayers.attn_cfgs.num_heads
         if self.num_heads != 8 or n_heads != 8:
             raise NotImplementedError("the CUDA library is compiled for 8 heads x 32")
+        # everything else the kernels hard-code is rejected here rather than silently mis-computed
+        for name, dec in (("transformer_decoder", transformer_decoder), ("relation_decoder", relation_decoder)):
+            tl = dec.transformerlayers
+            if tl.attn_cfgs.num_heads != 8 or tl.attn_cfgs.embed_dims != nat.EMBED_DIMS:
+                raise NotImplementedError(f"{name}: the CUDA library is compiled for 8 heads x 32 (embed_dims 256)")
+            if tuple(tl.operation_order) != ("cross_attn", "norm", "self_attn", "norm", "ffn", "norm"):
+                raise NotImplementedError(f"{name}: only operation_order (cross_attn, norm, self_attn, norm, ffn, norm)")
+            if tl.ffn_cfgs.get("act_cfg", dict(type="ReLU")).get("type") != "ReLU":
+                raise NotImplementedError(f"{name}: only ReLU FFNs")
+        pe = positional_encoding
+        if (pe.get("type") != "SinePositionalEncoding" or not pe.get("normalize", False)
+                or pe.get("temperature", 10000) != 10000 or abs(pe.get("scale", 2 * 3.141592653589793) - 2 * 3.141592653589793) > 1e-9
+                or pe.get("offset", 0.0) != 0.0 or pe.get("eps", 1e-6) != 1e-6):
+            raise NotImplementedError("positional_encoding: the CUDA kernel implements SinePositionalEncoding(normalize=True, "
+                                      "temperature=10000, scale=2*pi, offset=0, eps=1e-6) only")
         self.with_pixel_decoder = pixel_decoder is not None
         if self.with_pixel_decoder:
             assert pixel_decoder.encoder.transformerlayers.attn_cfgs.num_levels == num_transformer_feat_level

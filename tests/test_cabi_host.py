@@ -110,6 +110,33 @@ def test_registry_surface_and_state_dict_names():
     osd = OPSGTr().state_dict()
     assert set(osd.keys()) == keys
     assert all(osd[k].shape == sd[k].shape for k in keys)
+    # mmdet's SeesawLoss (rel_cls_loss) keeps a persistent buffer: every reference checkpoint carries it, so the documented
+    # `model.load_state_dict(ckpt["state_dict"])` (strict=True) must find a home for it
+    assert "bbox_head.rel_cls_loss.cum_samples" in keys and tuple(sd["bbox_head.rel_cls_loss.cum_samples"].shape) == (57,)
+    assert not any(k.startswith("bbox_head.loss_") or "subobj_cls_loss" in k or "importance_match_loss" in k for k in keys)
+    model.load_state_dict(osd, strict=True)
+
+
+def test_unsupported_geometry_is_rejected_not_miscomputed():
+    """What the kernels hard-code (8 heads x 32, post-norm op order, the sine encoding's constants) must raise."""
+    import copy
+    from pairnet_b200.registry import build_head
+    from tests.util import product_head_cfg
+    base = product_head_cfg()
+    base["pixel_decoder"] = None
+    build_head(copy.deepcopy(base))
+    bad = copy.deepcopy(base)
+    bad["relation_decoder"]["transformerlayers"]["attn_cfgs"]["num_heads"] = 4
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
+    bad = copy.deepcopy(base)
+    bad["positional_encoding"] = dict(type="SinePositionalEncoding", num_feats=128, normalize=False)
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
+    bad = copy.deepcopy(base)
+    bad["positional_encoding"] = dict(type="SinePositionalEncoding", num_feats=128, normalize=True, temperature=20)
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
 
 
 def test_reference_config_loads_unchanged_if_present():

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import (GOLDEN, RTOL_LOGITS, check_topk_tie_aware, oracle_small_head, product_small_head, rel_err)
+from tests.util import (GOLDEN, RTOL_LOGITS, TIE_RTOL, check_topk_tie_aware, elem_rel_err, oracle_downstream_from_pairs,
+                        oracle_small_head, product_small_head, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -47,18 +48,22 @@ def test_head_matches_oracle_and_golden(heads, case):
     # --- PPN
     assert rel_err(taps["importance_raw"], tr["importance_raw"]) < RTOL_LOGITS
     assert rel_err(cls["importance"], ocls["importance"]) < RTOL_LOGITS
-    tol = RTOL_LOGITS * float(ocls["importance"].abs().max())
+    tol = TIE_RTOL * float(ocls["importance"].abs().max())
     swapped = check_topk_tie_aware(ocls["importance"], taps["sub_pos"], taps["obj_pos"], tr["sub_pos"], tr["obj_pos"], tol)
-    assert swapped <= 4
-    # --- relation fusion + logits (north_star: 1e-3 relative on fp32 logits)
-    if swapped == 0:
-        assert rel_err(taps["pair_feat"], tr["pair_feat"].transpose(0, 1)) < RTOL_LOGITS
-        assert rel_err(taps["rel_feat"], tr["rel_feat"][-1].transpose(0, 1)) < RTOL_LOGITS
-        assert rel_err(cls["rel"], ocls["rel"]) < RTOL_LOGITS
-        assert rel_err(cls["sub"], ocls["sub"]) < RTOL_LOGITS
-        assert rel_err(cls["obj"], ocls["obj"]) < RTOL_LOGITS
-        assert rel_err(msk["sub_seg"], omsk["sub_seg"]) < RTOL_LOGITS
+    assert swapped == 0, f"{swapped} pairs differ from the oracle's top-k (all within the 1e-5 near-tie allowance)"
+    # --- relation fusion + logits (north_star: 1e-3 relative on fp32 logits); the oracle's downstream is evaluated
+    #     for the selected pairs, so nothing is skipped
+    od = oracle_downstream_from_pairs(o, tr, ocls, omsk, taps["sub_pos"], taps["obj_pos"])
+    assert torch.equal(od["rel"], ocls["rel"])  # the helper reproduces the oracle's own outputs for its own indices
+    assert rel_err(taps["pair_feat"], od["pair_feat"].transpose(0, 1)) < RTOL_LOGITS
+    assert rel_err(taps["rel_feat"], od["rel_feat"].transpose(0, 1)) < RTOL_LOGITS
+    for k in ("rel", "sub", "obj"):
+        assert rel_err(cls[k], od[k]) < RTOL_LOGITS, k
+        assert elem_rel_err(cls[k], od[k]) < RTOL_LOGITS, k
+    assert rel_err(msk["sub_seg"], od["sub_seg"]) < RTOL_LOGITS
+    assert rel_err(msk["obj_seg"], od["obj_seg"]) < RTOL_LOGITS
     assert rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
+    assert elem_rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
     assert rel_err(msk["mask"], omsk["mask"]) < RTOL_LOGITS
     # --- committed golden fixture (minted by oracle/make_golden.py)
     g = np.load(os.path.join(GOLDEN, f"head_small_{tag}.npz"))
@@ -66,10 +71,9 @@ def test_head_matches_oracle_and_golden(heads, case):
     assert rel_err(cls["importance"], g["importance"]) < RTOL_LOGITS
     assert rel_err(msk["mask"][:, :, ::4, ::4], g["mask_sub4"]) < RTOL_LOGITS
     assert rel_err(taps["query_out"], np.transpose(g["query_last"], (1, 0, 2))) < RTOL_LOGITS
-    if swapped == 0:
-        assert np.array_equal(taps["sub_pos"].cpu().numpy(), g["sub_pos"])
-        assert np.array_equal(taps["obj_pos"].cpu().numpy(), g["obj_pos"])
-        assert rel_err(cls["rel"], g["rel"]) < RTOL_LOGITS
+    assert np.array_equal(taps["sub_pos"].cpu().numpy(), g["sub_pos"])  # north_star: top-k indices bit-exact
+    assert np.array_equal(taps["obj_pos"].cpu().numpy(), g["obj_pos"])
+    assert rel_err(cls["rel"], g["rel"]) < RTOL_LOGITS
 
 
 def test_stage_ppn_and_relation_fusion_from_oracle_inputs(heads):
@@ -160,10 +164,11 @@ def test_full_size_properties(heads):
     assert all(torch.isfinite(v).all() for v in list(cls.values()) + list(msk.values()))
 
 
-def test_full_size_single_image_vs_oracle(heads):
-    """One 800x1333-sized image through the CPU oracle (a few seconds) vs the CUDA path."""
+@pytest.mark.parametrize("B,seed", [(1, 41), (2, 43)])
+def test_full_size_vs_oracle(heads, B, seed):
+    """800x1333-sized images (BASELINE config 2: bs = 2) through the CPU oracle (a few seconds per image) vs the CUDA path."""
     o, p = heads
-    mf, mems = _full_size_inputs(1, 41)
+    mf, mems = _full_size_inputs(B, seed)
     tr = {}
     with torch.no_grad():
         ocls, omsk = o.forward_from_memories(mf, mems, trace=tr)
@@ -173,10 +178,16 @@ def test_full_size_single_image_vs_oracle(heads):
     assert rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
     assert rel_err(msk["mask"], omsk["mask"]) < RTOL_LOGITS
     assert rel_err(cls["importance"], ocls["importance"]) < RTOL_LOGITS
-    tol = RTOL_LOGITS * float(ocls["importance"].abs().max())
+    tol = TIE_RTOL * float(ocls["importance"].abs().max())
     swapped = check_topk_tie_aware(ocls["importance"], taps["sub_pos"], taps["obj_pos"], tr["sub_pos"], tr["obj_pos"], tol)
+    # a near-tie swap (within 1e-5 of the scale) is legitimate at this size: the downstream is then checked against the
+    # oracle evaluated for the selected pairs -- never skipped
+    od = oracle_downstream_from_pairs(o, tr, ocls, omsk, taps["sub_pos"], taps["obj_pos"])
     if swapped == 0:
-        assert rel_err(cls["rel"], ocls["rel"]) < RTOL_LOGITS
+        assert torch.equal(od["rel"], ocls["rel"])
+    for k in ("rel", "sub", "obj"):
+        assert rel_err(cls[k], od[k]) < RTOL_LOGITS, (k, swapped)
+    assert rel_err(msk["sub_seg"], od["sub_seg"]) < RTOL_LOGITS
 
 
 def test_detector_end_to_end_small_image():
@@ -247,10 +258,14 @@ def test_head_other_query_counts_and_batches(N, R, B, hw4):
     assert rel_err(cls["cls"], ocls["cls"]) < RTOL_LOGITS
     assert rel_err(msk["mask"], omsk["mask"]) < RTOL_LOGITS
     assert rel_err(cls["importance"], ocls["importance"]) < RTOL_LOGITS
-    tol = RTOL_LOGITS * float(ocls["importance"].abs().max())
+    tol = TIE_RTOL * float(ocls["importance"].abs().max())
     swapped = check_topk_tie_aware(ocls["importance"], taps["sub_pos"], taps["obj_pos"], tr["sub_pos"], tr["obj_pos"], tol)
+    od = oracle_downstream_from_pairs(o, tr, ocls, omsk, taps["sub_pos"], taps["obj_pos"])
     if swapped == 0:
-        assert rel_err(cls["rel"], ocls["rel"]) < RTOL_LOGITS
+        assert torch.equal(od["rel"], ocls["rel"])
+    for k in ("rel", "sub", "obj"):
+        assert rel_err(cls[k], od[k]) < RTOL_LOGITS, (k, swapped)
+    assert rel_err(msk["sub_seg"], od["sub_seg"]) < RTOL_LOGITS
 
 
 def test_overlap_and_tensor_core_options_are_result_neutral(heads):
@@ -303,9 +318,7 @@ def test_channels_last_mask_features_and_mask_tc_option(heads):
 
 def _ref_cases():
     from oracle.pin_reference import REF_CASES
-    # the 200-query fixture pins the ORACLE to the reference (CPU tests); on the GPU the 200-query head is compared with
-    # the oracle directly (test_head_other_query_counts_and_batches), without the <= 4 near-tie swap allowance used here
-    return [c for c in REF_CASES if c[4] <= 100]
+    return list(REF_CASES)  # all four, including the 200 object / 200 relation query case (BASELINE config 4)
 
 
 @pytest.mark.parametrize("tag,B,hw4,seed,N,R", _ref_cases())
@@ -331,14 +344,31 @@ def test_head_matches_reference_forward_golden(tag, B, hw4, seed, N, R):
     assert rel_err(cls["cls"], g["cls"]) < RTOL_LOGITS
     assert rel_err(cls["importance"], g["importance"]) < RTOL_LOGITS
     assert rel_err(msk["mask"][:, :, ::4, ::4], g["mask_sub4"]) < RTOL_LOGITS
-    tol = RTOL_LOGITS * float(np.abs(g["importance"]).max())
+    # north_star: top-k indices bit-exact against the reference's own forward.  The only admissible difference is a swap
+    # of two pairs whose REFERENCE values are closer than 1e-5 of the scale (the 200-query fixture has one such pair at
+    # ranks 195/196: 0.04868449 vs 0.04868435, 2 ulp apart -- no summation order other than the reference's own
+    # reproduces it); anything else fails inside check_topk_tie_aware.
+    tol = TIE_RTOL * float(np.abs(g["importance"]).max())
     swapped = check_topk_tie_aware(g["importance"], taps["sub_pos"], taps["obj_pos"], g["sub_pos"], g["obj_pos"], tol)
-    assert swapped <= 4
-    if swapped == 0:   # top-k indices bit-exact -> every downstream tensor is comparable
+    assert swapped <= 2, swapped
+    if swapped == 0:
         assert np.array_equal(taps["sub_pos"].cpu().numpy(), g["sub_pos"])
         assert np.array_equal(taps["obj_pos"].cpu().numpy(), g["obj_pos"])
-        assert rel_err(cls["rel"], g["rel"]) < RTOL_LOGITS
-        assert rel_err(cls["sub"], g["sub"]) < RTOL_LOGITS
-        assert rel_err(cls["obj"], g["obj"]) < RTOL_LOGITS
-        assert rel_err(msk["sub_seg"][:, :, ::4, ::4], g["sub_seg_sub4"]) < RTOL_LOGITS
-        assert rel_err(msk["obj_seg"][:, :, ::4, ::4], g["obj_seg_sub4"]) < RTOL_LOGITS
+        ref = {k: torch.from_numpy(g[k]) for k in ("rel", "sub", "obj")}
+        ref_sub_seg, ref_obj_seg = g["sub_seg_sub4"], g["obj_seg_sub4"]
+    else:
+        # downstream tensors depend on the pair order: evaluate the oracle (bit-equal to the reference on this case,
+        # tests/test_oracle_golden.py) for the pairs the CUDA path selected -- nothing is skipped
+        shell.load_state_dict(fixture_state_dict(shell, 10086))
+        shell.eval()
+        tr = {}
+        with torch.no_grad():
+            ocls, omsk = shell.forward_from_memories(mf, mems, trace=tr)
+        assert np.array_equal(ocls["importance"].numpy(), g["importance"])
+        ref = oracle_downstream_from_pairs(shell, tr, ocls, omsk, taps["sub_pos"], taps["obj_pos"])
+        ref_sub_seg, ref_obj_seg = ref["sub_seg"][:, :, ::4, ::4], ref["obj_seg"][:, :, ::4, ::4]
+    for k in ("rel", "sub", "obj"):
+        assert rel_err(cls[k], ref[k]) < RTOL_LOGITS, k
+        assert elem_rel_err(cls[k], ref[k]) < RTOL_LOGITS, k
+    assert rel_err(msk["sub_seg"][:, :, ::4, ::4], ref_sub_seg) < RTOL_LOGITS
+    assert rel_err(msk["obj_seg"][:, :, ::4, ::4], ref_obj_seg) < RTOL_LOGITS

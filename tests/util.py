@@ -8,13 +8,57 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 RTOL_LOGITS = 1e-3  # BASELINE.json north_star: "within 1e-3 relative for fp32 logits"
+# Near-tie allowance of the top-k comparison: two ORACLE values closer than this (relative to max|importance|) may
+# legitimately swap under a different fp32 summation order.  The measured importance error of the CUDA path is
+# ~3.5e-6 of the scale, so 1e-5 (the bar the stage test always used) is ~3x that, not 300x.
+TIE_RTOL = 1e-5
 
 
 def rel_err(a, b):
-    """max|a-b| / max|b|  (the 'relative' of the 1e-3 logits bar: normalised by the tensor's scale)."""
+    """max|a-b| / max|b|: a SCALE-relative norm (normalised by the tensor's largest magnitude), not element-wise
+    relative -- the reading of north_star's "1e-3 relative for fp32 logits" that is meaningful for logits crossing
+    zero.  ``elem_rel_err`` below is the element-wise companion for the entries that are not near zero."""
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def elem_rel_err(a, b, floor_frac=1e-2):
+    """max over elements with |b| > floor_frac * max|b| of |a-b| / |b|  (element-wise relative error)."""
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    keep = b.abs() > floor_frac * b.abs().max()
+    if not bool(keep.any()):
+        return 0.0
+    return float(((a - b).abs()[keep] / b.abs()[keep]).max())
+
+
+def oracle_downstream_from_pairs(o, tr, ocls, omsk, sub_pos, obj_pos):
+    """The ORACLE's pair-dependent outputs (pairnet_head.py:342-403: pair gather, Relation Fusion, classifier, output
+    gathers) recomputed for GIVEN pair indices.  With the oracle's own indices this reproduces its outputs; with the
+    CUDA path's indices it keeps every downstream tensor checkable when a near-tie legitimately swapped two pairs."""
+    sub_pos = torch.as_tensor(sub_pos).cpu()
+    obj_pos = torch.as_tensor(obj_pos).cpu()
+    q = tr["query_feat"][-1]  # [N,B,256]
+    B = q.shape[1]
+    E = q.shape[-1]
+    with torch.no_grad():
+        objf = torch.gather(q, 0, obj_pos.unsqueeze(-1).repeat(1, 1, E).transpose(0, 1))
+        subf = torch.gather(q, 0, sub_pos.unsqueeze(-1).repeat(1, 1, E).transpose(0, 1))
+        pair = torch.cat([subf, objf], dim=0)
+        x = o.rel_query_feat.weight.unsqueeze(1).repeat((1, B, 1))
+        qe = o.rel_query_embed.weight.unsqueeze(1).repeat((1, B, 1))
+        ke = o.rel_query_embed2.weight.unsqueeze(1).repeat((1, B, 1))
+        ve = o.rel_query_embed3.weight.unsqueeze(1).repeat((1, B, 1))
+        for layer in o.relation_decoder.layers:
+            x = layer(query=x, key=pair, value=pair, query_pos=qe, key_pos=ke, value_pos=ve)
+        rel = o.rel_cls_embed(x.transpose(0, 1))
+        cls, mask = ocls["cls"], omsk["mask"]
+        sub = torch.gather(cls, 1, sub_pos.unsqueeze(-1).expand(-1, -1, cls.shape[-1]))
+        obj = torch.gather(cls, 1, obj_pos.unsqueeze(-1).expand(-1, -1, cls.shape[-1]))
+        sub_seg = torch.gather(mask, 1, sub_pos[..., None, None].expand(-1, -1, mask.shape[-2], mask.shape[-1]))
+        obj_seg = torch.gather(mask, 1, obj_pos[..., None, None].expand(-1, -1, mask.shape[-2], mask.shape[-1]))
+    return dict(pair_feat=pair, rel_feat=x, rel=rel, sub=sub, obj=obj, sub_seg=sub_seg, obj_seg=obj_seg)
 
 
 def oracle_small_head(seed=10086, dtype=torch.float32):
