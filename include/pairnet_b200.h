@@ -95,6 +95,9 @@ PN_API int pn_get_option(int key);
                                    6 layers + classifier);  1 (default) = that chain from 8 images per call (it runs 8 SMs per
                                    image), below per-op kernels on all SMs with the cross attention on tcgen05 (fa_umma.cu);
                                    0 = round-1 per-op kernels (warp-MMA linears, FFMA attention), prepared blob unused */
+#define PN_OPT_PPN_FUSED_TOPK 11 /* default 1: micro-benchmark mode of pn_ppn_forward (no MLPs, no ConvTiny, no pair_feat) with >= 1024
+                                    embedding rows: pair matrix and top-k in ONE tcgen05 kernel (pair_topk.cu), the matrix is written
+                                    once and never read back; 0 = pair-matrix kernel followed by the stand-alone top-k kernel */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

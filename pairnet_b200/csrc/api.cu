@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {
@@ -584,6 +584,7 @@ static int ppn_forward(const float* query, const float* query_obj, const PnMlp3*
   if (!raw) raw = conv ? ws.take<float>((size_t)B * N * N) : importance;
   const size_t conv_bytes = conv ? conv_tiny_workspace_bytes(B, N, conv->mid_channels) : 0;
   char* conv_ws = conv ? ws.take<char>(conv_bytes) : nullptr;
+  int* redo = ws.take<int>((size_t)B);
   PN_REQUIRE(ws.ok() && !ws.dry, PN_ERR_WORKSPACE, "ppn: workspace too small");
 
   if (sub_mlp) {
@@ -617,6 +618,13 @@ static int ppn_forward(const float* query, const float* query_obj, const PnMlp3*
     return launch_gemm(g, st);
   };
   const size_t img_bytes = sizeof(float) * (size_t)N * N;
+  if (tc && !conv && raw == importance && !pair_feat && get_option(OPT_PPN_FUSED_TOPK) &&
+      pair_topk_fused_supported(N, D, K)) {
+    // micro-benchmark 5a at scale: ONE pass over HBM -- the top-k runs on the tensor-memory accumulator inside the
+    // pair-matrix kernel; images it flags (candidate overflow: constant / adversarial matrices) go to the exact kernel
+    PN_TRY(launch_pair_topk_fused(S, O, importance, topk_idx, sub_pos, obj_pos, redo, B, N, D, K, st));
+    return launch_topk_pairs(importance, topk_idx, sub_pos, obj_pos, query, nullptr, B, N, K, st, redo);
+  }
   if (!conv && raw == importance && (size_t)B * img_bytes > PPN_L2_CHUNK_BYTES) {
     // large batches (micro-benchmark 5a): walk the batch in chunks whose pair matrices stay resident in the 126 MB
     // L2 between the kernel that writes them and the top-k kernel that reads them back
@@ -649,6 +657,7 @@ static size_t ppn_bytes(int B, int N, int K, int mid) {
   for (int i = 0; i < 4; ++i) ws.take<float>((size_t)2 * M * D);
   ws.take<float>((size_t)B * N * N);
   ws.take<char>(conv_tiny_workspace_bytes(B, N, mid > 0 ? mid : 64));
+  ws.take<int>((size_t)B);
   return ws.off + 1024;
 }
 

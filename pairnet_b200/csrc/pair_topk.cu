@@ -1,0 +1,493 @@
+// Pair Proposal Network at scale (BASELINE config 5a): pair matrix + top-k pair select in ONE pass over HBM.
+//
+//   importance[b] = S[b] . O[b]^T              (pairnet_head.py:327)
+//   idx = topk(importance[b].flatten(), K)     (pairnet_head.py:334-336; descending, ties by ascending flat index)
+//   sub_pos = idx / N, obj_pos = idx % N       (pairnet_head.py:337-340)
+//
+//   S, O : [B, N, 256] fp32 (L2-normalised subject / object embeddings);  importance [B, N, N] fp32;  int64 indices.
+//
+// One persistent CTA per SM owns whole images.  The matrix of an image is produced tile by tile (128 rows x bn <= 256
+// columns) on tcgen05 as 3xTF32 and is written to HBM exactly once; the top-k never reads it back:
+//
+//   warp 0      TMA producer: raw fp32 k-blocks (32 channels = one 128-byte swizzle row) of S and O through 3-D maps
+//               [B][N][256]; rows past N are zero-filled by the TMA unit (no padded copy, no bytes of the next image).
+//               The raw ring is as deep as shared memory allows (5 stages at N = 100): the kernel is bound by bytes in
+//               flight per SM, so raw tiles are kept apart from the short-lived lo tiles (2 slots).
+//   warps 6-13  splitters: the tensor pipe reads fp32 containers as TF32 by IGNORING the low 13 mantissa bits, so the
+//               raw tile IS the hi operand (hi = trunc(x)); only lo = x - trunc(x) (exact in fp32, nudged by half a
+//               TF32 ulp so that the hardware truncation rounds it to nearest) is written, to a twin tile with the
+//               identical swizzled layout.
+//   warp 1      MMA issuer: lo*hi + hi*lo + hi*hi, tcgen05.mma kind::tf32, M = 128, N = bn, two ping-pong TMEM
+//               accumulators.
+//   warps 2-5   epilogue (one matrix row per thread): tcgen05.ld -> store the valid corner -> threshold top-k on the
+//               accumulator itself:
+//                 first tile of an image: two order-key maxima per row (left / right half of the tile) -> t0 = K-th
+//                 largest of the 256 local maxima.  They are K distinct matrix elements >= t0, so { x >= t0 } contains
+//                 the whole top-K; a second read of the tile from TMEM compacts those candidates (key << 32 | ~flat
+//                 index) into shared memory.  Later tiles of the image push candidates in their single pass.
+//                 last tile: rank the candidates by counting (the composite order IS the output order), write int64s.
+//               Images whose candidate set overflows (adversarial: constant matrices) or that cannot be thresholded
+//               set redo[b] = 1; the caller runs the stand-alone exact kernel (`launch_topk_pairs`) on those.
+//
+// HBM traffic per image is the algorithmic 2*N*256*4 B in + N*N*4 B + 2(3)*K*8 B out; operand re-reads of images with
+// more than one tile (N > 128) come from L2.
+#include "umma_ptx.cuh"
+
+namespace pn {
+namespace pairtopk {
+
+using namespace umma;
+
+constexpr int BM = 128, BK = 32;
+constexpr int NUM_SPLIT_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + 32 * NUM_SPLIT_WARPS;  // warp0 TMA, warp1 MMA, 2-9 epilogue, 10-17 splitters
+constexpr int LO_SLOTS = 2;
+constexpr int TOPK_MAX = 256, CAND_MAX = 1536;
+constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
+constexpr int TAIL_PAD = 2048;      // MMA row over-reads past the last tile (< 16 rows >= N: results never stored) stay inside
+
+struct TopkSmem {
+  unsigned long long cand[CAND_MAX];
+  unsigned long long win[TOPK_MAX];
+  uint32_t lm[2 * BM];
+  uint32_t t0;
+  unsigned ncand;
+};
+constexpr int CTRL_BYTES = 256;  // mbarriers + TMEM base slot
+constexpr int STAGE_TILE = 32 * 128;  // one 32-row x 32-column fp32 output tile (SWIZZLE_128B)
+
+struct Params {
+  CUtensorMap s_map, o_map;  // [B][N][K]; boxes 32 x s_box x 1 and 32 x o_box x 1
+  CUtensorMap c_map;         // [B][N][N]; box 32 x 32 x 1 (store)
+  float* C;                  // [B, N, N]
+  int64_t *topk_idx, *sub_pos, *obj_pos;  // [B, topk] (topk_idx may be null)
+  int* redo;                 // [B]
+  int B, N, K, topk;
+  int mtiles, ntiles;
+  int n_step, bn;            // n-tile origin = nt * n_step (multiple of 8); bn = MMA N extent (n_step rounded up to 16, <= 256)
+  int s_tile, o_tile;        // bytes of one raw k-block tile of S / O (multiples of 1024)
+  int raw_stages;            // depth of the raw ring
+  int acc_stride;            // TMEM columns between the two accumulators
+  int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ unsigned long long composite(uint32_t key, uint32_t idx) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// lo part of the 3xTF32 split when the hi part is the hardware's own truncation of x
+__device__ __forceinline__ float lo_of(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return __uint_as_float(__float_as_uint(x - hi) + 0x1000u);  // + half a TF32 ulp: truncation then rounds to nearest
+}
+
+struct Ring {  // (slot, phase) walker over a ring of runtime depth
+  int slot, depth;
+  uint32_t phase;
+  __device__ __forceinline__ Ring(int d) : slot(0), depth(d), phase(0) {}
+  __device__ __forceinline__ void next() {
+    if (++slot == depth) { slot = 0; phase ^= 1u; }
+  }
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_constant__ Params prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  const int stage_bytes = prm.s_tile + prm.o_tile;
+  const int RS = prm.raw_stages;
+  uint8_t* raw_ring = smem;
+  uint8_t* lo_ring = smem + (size_t)RS * stage_bytes;
+  uint8_t* out_stage = lo_ring + (size_t)LO_SLOTS * stage_bytes + TAIL_PAD;  // [8 warps][32 rows x 128 B], swizzled
+  uint8_t* ctrl = out_stage + NUM_EPI_WARPS * STAGE_TILE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [RS<=8] TMA -> splitters
+  uint64_t* empty_bar = full_bar + 8;                       // [RS<=8] MMA -> TMA
+  uint64_t* split_bar = empty_bar + 8;                      // [2] splitters -> MMA
+  uint64_t* lo_empty_bar = split_bar + 2;                   // [2] MMA -> splitters
+  uint64_t* tmem_full_bar = lo_empty_bar + 2;               // [2] MMA -> epilogue
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2] epilogue -> MMA
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  TopkSmem& tk = *reinterpret_cast<TopkSmem*>(ctrl + CTRL_BYTES);
+
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < RS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&split_bar[a], NUM_SPLIT_WARPS);
+      mbar_init(&lo_empty_bar[a], 1);
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"(prm.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_base_slot);
+  const int num_kb = prm.K / BK;
+  const int tiles_per_img = prm.mtiles * prm.ntiles;
+  const int N = prm.N;
+
+  if (warp == 0) {
+    // ===== TMA producer (warp-uniform loop, one elected lane issues)
+    Ring r(RS);
+    const uint32_t stage_tx = (uint32_t)stage_bytes;
+    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+      for (int t = 0; t < tiles_per_img; ++t) {
+        const int m0 = (t / prm.ntiles) * BM, n0 = (t % prm.ntiles) * prm.n_step;
+        for (int kb = 0; kb < num_kb; ++kb, r.next()) {
+          mbar_wait(&empty_bar[r.slot], r.phase ^ 1u);
+          uint8_t* st = raw_ring + (size_t)r.slot * stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[r.slot], stage_tx);
+            tma_load_3d(st, &prm.s_map, &full_bar[r.slot], kb * BK, m0, b);
+            tma_load_3d(st + prm.s_tile, &prm.o_map, &full_bar[r.slot], kb * BK, n0, b);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform loop, one elected lane issues)
+    const uint32_t idesc = make_idesc(prm.bn);
+    Ring r(RS), l(LO_SLOTS);
+    uint32_t tile_it = 0;
+    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+      for (int t = 0; t < tiles_per_img; ++t, ++tile_it) {
+        const uint32_t acc = tile_it & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)prm.acc_stride;
+        for (int kb = 0; kb < num_kb; ++kb, r.next(), l.next()) {
+          mbar_wait(&split_bar[l.slot], l.phase);  // lo tiles written (and, transitively, the raw tiles landed)
+          tc_fence_after();
+          const uint32_t hi = smem_u32(raw_ring + (size_t)r.slot * stage_bytes);
+          const uint32_t lo = smem_u32(lo_ring + (size_t)l.slot * stage_bytes);
+          const uint64_t a_hi = make_smem_desc(hi), b_hi = make_smem_desc(hi + prm.s_tile);
+          const uint64_t a_lo = make_smem_desc(lo), b_lo = make_smem_desc(lo + prm.s_tile);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+              const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
+              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            }
+            umma_commit(&empty_bar[r.slot]);
+            umma_commit(&lo_empty_bar[l.slot]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + NUM_EPI_WARPS) {
+    // ===== epilogue + top-k: 8 warps.  TMEM lane quadrant = warp % 4 (one matrix row per thread); the two warps of a
+    // quadrant take alternate 32-column chunks (par).  Everything below is latency bound at one warp per scheduler, so
+    // the work per element is kept to one or two instructions: float compares against the threshold, keys only for
+    // the (rare) candidates.
+    const int quad = warp & 3;
+    const int par = (warp - 2) >> 2;
+    const int et = par * BM + quad * 32 + lane;  // 0 .. 255
+    const int K = prm.topk;
+    uint8_t* sbuf = out_stage + (size_t)(warp - 2) * STAGE_TILE;  // one 32 x 32 fp32 staging tile per epilogue warp
+    const float NEG_INF = __uint_as_float(0xff800000u);
+    const uint32_t KEY_NEG_INF = order_key(NEG_INF);
+    uint32_t tile_it = 0;
+    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+      bool have_t0 = false;
+      uint32_t t0 = 0;
+      float t0f = 0.f;
+      if (et == 0) tk.ncand = 0;  // first push happens after the epi_sync that publishes t0
+      for (int t = 0; t < tiles_per_img; ++t, ++tile_it) {
+        const int m0 = (t / prm.ntiles) * BM, n0 = (t % prm.ntiles) * prm.n_step;
+        const uint32_t acc = tile_it & 1;
+        mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
+        tc_fence_after();
+        const int row = m0 + quad * 32 + lane;
+        const bool rvalid = row < N;
+        const bool wvalid = m0 + quad * 32 < N;  // this warp's 32-row slab holds at least one matrix row
+        const int ncols = min(prm.n_step, N - n0);  // valid columns of this n-tile
+        const uint32_t flat0 = (uint32_t)row * (uint32_t)N + (uint32_t)n0;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)prm.acc_stride;
+        float lm = NEG_INF;
+#pragma unroll 1
+        for (int c0 = 32 * par; c0 < ncols; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tbase + (uint32_t)c0, v);
+          // ---- store: 32 rows x 32 columns through this warp's swizzled staging tile and ONE TMA store (rows / columns
+          // past N are clipped by the tensor map); a thread-per-row STG would touch 32 lines per instruction
+          if (wvalid) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile's previous store
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                              __uint_as_float(v[4 * j + 3]));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&prm.c_map, sbuf, n0 + c0, m0 + quad * 32, b);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (rvalid) {
+            const int nv = ncols - c0;  // valid columns of this chunk (>= 32: all)
+            if (have_t0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = __uint_as_float(v[j]);
+                if (!(x < t0f) && j < nv) {  // NaN passes; the composite key ranks it
+                  const unsigned slot = atomicAdd(&tk.ncand, 1u);
+                  if (slot < CAND_MAX) tk.cand[slot] = composite(order_key(x), flat0 + (uint32_t)(c0 + j));
+                }
+              }
+            } else if (nv >= 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) lm = fmaxf(lm, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) lm = fmaxf(lm, j < nv ? __uint_as_float(v[j]) : NEG_INF);
+            }
+          }
+        }
+        if (!have_t0) {
+          // ---- threshold: K-th largest of the 256 local maxima (row x chunk parity) of the image's first tile.  The low
+          // 8 key bits are replaced by the slot number: all entries distinct (one counting pass gives the rank) and the
+          // threshold only moves down by < 256 ulps, so { x >= t0 } still contains the whole top-K.
+          const uint32_t mykey = (order_key(lm) & 0xffffff00u) | (uint32_t)(255 - et);
+          tk.lm[et] = mykey;
+          epi_sync();
+          unsigned g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+#pragma unroll 8
+          for (int j = 0; j < 2 * BM; j += 4) {
+            const uint4 m = *reinterpret_cast<const uint4*>(&tk.lm[j]);
+            g0 += m.x > mykey; g1 += m.y > mykey; g2 += m.z > mykey; g3 += m.w > mykey;
+          }
+          if (g0 + g1 + g2 + g3 == (unsigned)(K - 1)) tk.t0 = mykey & 0xffffff00u;
+          epi_sync();
+          t0 = tk.t0;
+          t0f = key_to_float(t0);
+          have_t0 = true;
+          // ---- candidates of the first tile: second read of the accumulator
+          if (t0 > (KEY_NEG_INF | 0xffu)) {  // else: fewer than K valid local maxima -> the image goes to the exact kernel
+#pragma unroll 1
+            for (int c0 = 32 * par; c0 < ncols; c0 += 64) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(tbase + (uint32_t)c0, v);
+              if (rvalid) {
+                const int nv = ncols - c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float x = __uint_as_float(v[j]);
+                  if (!(x < t0f) && j < nv) {
+                    const unsigned slot = atomicAdd(&tk.ncand, 1u);
+                    if (slot < CAND_MAX) tk.cand[slot] = composite(order_key(x), flat0 + (uint32_t)(c0 + j));
+                  }
+                }
+              }
+            }
+          }
+        }
+        // accumulator drained: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (t == tiles_per_img - 1) {
+          epi_sync();
+          const unsigned nc = tk.ncand;
+          const bool bad = t0 <= (KEY_NEG_INF | 0xffu) || nc > (unsigned)CAND_MAX || nc < (unsigned)K;
+          if (et == 0) prm.redo[b] = bad ? 1 : 0;
+          if (!bad) {
+            // ---- rank by counting: win[r] = candidate with r larger candidates
+            for (unsigned i = et; i < nc; i += 32 * NUM_EPI_WARPS) {
+              const unsigned long long me = tk.cand[i];
+              unsigned r0 = 0, r1 = 0;
+              unsigned j = 0;
+#pragma unroll 4
+              for (; j + 1 < nc; j += 2) {
+                const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(&tk.cand[j]);
+                r0 += c.x > me; r1 += c.y > me;
+              }
+              if (j < nc) r0 += tk.cand[j] > me;
+              if (r0 + r1 < (unsigned)K) tk.win[r0 + r1] = me;
+            }
+            epi_sync();
+            for (int r = et; r < K; r += 32 * NUM_EPI_WARPS) {
+              const uint32_t idx = 0xffffffffu - (uint32_t)(tk.win[r] & 0xffffffffull);
+              const size_t o = (size_t)b * K + r;
+              if (prm.topk_idx) prm.topk_idx[o] = (long long)idx;
+              prm.sub_pos[o] = (long long)(idx / (uint32_t)N);
+              prm.obj_pos[o] = (long long)(idx % (uint32_t)N);
+            }
+          }
+          epi_sync();  // smem of this image is recycled by the next one
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tiles outlive their stores
+    tc_fence_before();
+  } else {
+    // ===== splitters: lo tiles of S and O (16-byte chunks, swizzled layout preserved); the raw tile is the hi operand
+    const int sid = threadIdx.x - (64 + 32 * NUM_EPI_WARPS);  // 0 .. 255
+    constexpr int NSPLIT = 32 * NUM_SPLIT_WARPS;
+    Ring r(RS), l(LO_SLOTS);
+    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+      for (int t = 0; t < tiles_per_img; ++t) {
+        // only rows that exist are split (8 chunks of 16 B per row; the swizzle permutes chunks inside a row only).
+        // Rows past N are zero in the raw tile (TMA fill) or lie past it; whatever the lo tile holds there only
+        // reaches output rows / columns >= N, which are never stored nor ranked.
+        const int m0 = (t / prm.ntiles) * BM, n0 = (t % prm.ntiles) * prm.n_step;
+        const int chunks_s = ((min(BM, N - m0) + 7) & ~7) * 8;
+        const int chunks_o = ((min(prm.n_step, N - n0) + 7) & ~7) * 8;
+        const int o_shift = prm.s_tile - chunks_s * 16;  // chunk index -> byte offset jump from the S to the O tile
+        for (int kb = 0; kb < num_kb; ++kb, r.next(), l.next()) {
+          mbar_wait(&full_bar[r.slot], r.phase);
+          mbar_wait(&lo_empty_bar[l.slot], l.phase ^ 1u);
+          const uint8_t* src = raw_ring + (size_t)r.slot * stage_bytes;
+          uint8_t* dst = lo_ring + (size_t)l.slot * stage_bytes;
+#pragma unroll 4
+          for (int c = sid; c < chunks_s + chunks_o; c += NSPLIT) {
+            const int off = c * 16 + (c >= chunks_s ? o_shift : 0);
+            const float4 x = *reinterpret_cast<const float4*>(src + off);
+            float4 y;
+            y.x = lo_of(x.x); y.y = lo_of(x.y); y.z = lo_of(x.z); y.w = lo_of(x.w);
+            *reinterpret_cast<float4*>(dst + off) = y;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[l.slot]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(prm.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map_3d(CUtensorMap* map, const float* ptr, int B, int N, int K, int box_rows, int box_cols = BK) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  PN_REQUIRE(fn, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  PN_REQUIRE(((uintptr_t)ptr & 15) == 0, PN_ERR_UNSUPPORTED, "pair top-k: embeddings must be 16B aligned");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)N * K * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace pairtopk
+
+// the fused kernel thresholds on 2 local maxima (even / odd 32-column chunks) per row of the image's first tile
+bool pair_topk_fused_supported(int N, int K, int topk) {
+  const int rows0 = N < pairtopk::BM ? N : pairtopk::BM;
+  return topk >= 1 && topk <= pairtopk::TOPK_MAX && topk <= (N > 32 ? 2 : 1) * rows0 && N >= 2 && (N & 3) == 0 &&
+         K % pairtopk::BK == 0 && K >= pairtopk::BK && (long long)N * N < (1ll << 31);
+}
+
+// importance[b] = S[b] . O[b]^T (3xTF32 on tcgen05) with the top-k pair select fused into the epilogue.
+// redo [B] int: set to 1 for images the caller must pass to `launch_topk_pairs` (exact kernel), 0 otherwise.
+int launch_pair_topk_fused(const float* S, const float* O, float* C, int64_t* topk_idx, int64_t* sub_pos,
+                           int64_t* obj_pos, int* redo, int B, int N, int K, int topk, cudaStream_t st) {
+  using namespace pairtopk;
+  PN_REQUIRE(S && O && C && sub_pos && obj_pos && redo && B > 0, PN_ERR_BAD_ARG, "pair top-k: bad args");
+  PN_REQUIRE(pair_topk_fused_supported(N, K, topk), PN_ERR_UNSUPPORTED, "pair top-k: N=%d K=%d topk=%d unsupported", N,
+             K, topk);
+  Params prm{};
+  prm.C = C; prm.topk_idx = topk_idx; prm.sub_pos = sub_pos; prm.obj_pos = obj_pos; prm.redo = redo;
+  prm.B = B; prm.N = N; prm.K = K; prm.topk = topk;
+  prm.mtiles = cdiv(N, BM);
+  // n-tiles of one image start at multiples of 32 columns: the epilogue stores 32-column boxes
+  prm.ntiles = (int)round_up(N, 8) <= 224 ? 1 : cdiv(N, 224);  // <= 224 columns: two raw stages + lo + staging fit smem
+  prm.n_step = prm.ntiles == 1 ? (int)round_up(N, 8) : (int)round_up(cdiv(N, prm.ntiles), 32);
+  prm.bn = (int)round_up(prm.n_step, 16);
+  const int s_box = (int)round_up(N < BM ? N : BM, 8);
+  const int o_box = prm.n_step;
+  prm.s_tile = s_box * BK * 4;
+  prm.o_tile = o_box * BK * 4;
+  PN_TRY(make_map_3d(&prm.s_map, S, B, N, K, s_box));
+  PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box));
+  PN_TRY(make_map_3d(&prm.c_map, C, B, N, N, 32, 32));
+  const int stage = prm.s_tile + prm.o_tile;
+  const int fixed = 1024 + TAIL_PAD + NUM_EPI_WARPS * STAGE_TILE + CTRL_BYTES + (int)sizeof(TopkSmem) + 64;
+  int rs = (SMEM_LIMIT - fixed) / stage - LO_SLOTS;
+  rs = rs > 8 ? 8 : rs;
+  PN_REQUIRE(rs >= 2, PN_ERR_UNSUPPORTED, "pair top-k: tiles of N=%d do not fit shared memory", N);
+  prm.raw_stages = rs;
+  prm.acc_stride = prm.bn <= 128 ? 128 : 256;
+  prm.tmem_cols = 2 * prm.acc_stride;
+  const size_t smem = (size_t)fixed + (size_t)(rs + LO_SLOTS) * stage;
+  static bool attr_done[PN_MAX_DEVICES] = {false};  // the attribute is per device
+  bool& attr_set = attr_done[current_device()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pair_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    PN_REQUIRE(e == cudaSuccess, (int)e, "pair top-k: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_sms = sm_count();
+  const int grid = B < num_sms ? B : num_sms;
+  pair_topk_kernel<<<grid, NUM_THREADS, smem, st>>>(prm);
+  return check_launch("pair_topk_kernel");
+}
+
+}  // namespace pn

@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(THREADS) topk_pairs_kernel(const float* __rest
                                                              int64_t* __restrict__ obj_pos,
                                                              const float* __restrict__ query,
                                                              float* __restrict__ pair_feat, int N, int K,
-                                                             int force_radix) {
+                                                             int force_radix,
+                                                             const int* __restrict__ only_if) {
   __shared__ uint32_t maxk[THREADS];
   __shared__ unsigned long long cand[CAND_MAX];
   __shared__ unsigned long long win[TOPK_MAXK];
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(THREADS) topk_pairs_kernel(const float* __rest
   __shared__ unsigned scal[4];
   __shared__ unsigned s_t0, s_ncand;
   const int b = blockIdx.x;
+  if (only_if && !only_if[b]) return;  // clean-up pass after the fused pair-matrix + top-k kernel (pair_topk.cu)
   const int tid = threadIdx.x, lane = tid & 31;
   const int NN = N * N;
   const float* v = imp + (size_t)b * NN;
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(THREADS) topk_pairs_kernel(const float* __rest
 }
 
 int launch_topk_pairs(const float* imp, int64_t* topk_idx, int64_t* sub_pos, int64_t* obj_pos, const float* query,
-                      float* pair_feat, int B, int N, int K, cudaStream_t st) {
+                      float* pair_feat, int B, int N, int K, cudaStream_t st, const int* only_if) {
   PN_REQUIRE(imp && sub_pos && obj_pos && B > 0 && N > 0, PN_ERR_BAD_ARG, "topk_pairs: bad args");
   PN_REQUIRE(K >= 1 && K <= TOPK_MAXK && (long long)K <= (long long)N * N, PN_ERR_UNSUPPORTED,
              "topk_pairs: K=%d unsupported (1..%d, <= N*N)", K, TOPK_MAXK);
@@ -457,11 +459,14 @@ int launch_topk_pairs(const float* imp, int64_t* topk_idx, int64_t* sub_pos, int
   const long long NN = (long long)N * N;
   const int force_radix = get_option(OPT_TOPK_RADIX) != 0;
   if (NN <= 16384)
-    topk_pairs_kernel<256><<<B, 256, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix);
+    topk_pairs_kernel<256><<<B, 256, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix,
+                                       only_if);
   else if (NN <= 65536)
-    topk_pairs_kernel<512><<<B, 512, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix);
+    topk_pairs_kernel<512><<<B, 512, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix,
+                                       only_if);
   else
-    topk_pairs_kernel<1024><<<B, 1024, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix);
+    topk_pairs_kernel<1024><<<B, 1024, 0, st>>>(imp, topk_idx, sub_pos, obj_pos, query, pair_feat, N, K, force_radix,
+                                       only_if);
   return check_launch("topk_pairs_kernel");
 }
 

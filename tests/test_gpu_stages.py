@@ -508,7 +508,8 @@ def test_backbone_fused_epilogue_path_matches_module_path():
 
 
 # --------------------------------------------------------------------------- PPN at scale (BASELINE config 5)
-@pytest.mark.parametrize("B,N", [(12, 100), (7, 200), (3, 400), (30, 37), (9, 128), (8, 130), (600, 100)])
+@pytest.mark.parametrize("B,N", [(12, 100), (7, 200), (3, 400), (30, 37), (9, 128), (8, 130), (600, 100), (5, 256),
+                                 (4, 388), (20, 64), (40, 48), (150, 104), (3, 512)])
 def test_pair_matrix_tcgen05_and_topk_batched(B, N):
     """Pair matrix on the tcgen05 kernel (both operands split in the SM, 3-D TMA with OOB zero fill) + batched
     top-k: importance to fp32 accuracy of the fp64 product, indices bit-exact for the matrix the kernel wrote."""
@@ -538,6 +539,43 @@ def test_pair_matrix_tcgen05_and_topk_batched(B, N):
     finally:
         nat.load().pn_set_option(7, 1)
     assert float((imp2 - imp).abs().max()) < 2e-6
+    # fused pair-matrix + top-k kernel (default where supported) == pair-matrix kernel followed by the top-k kernel
+    nat.load().pn_set_option(nat.PN_OPT_PPN_FUSED_TOPK, 0)
+    try:
+        imp3, idx3, sp3, op3 = [t.clone() for t in plan.run_embeds(s.cuda(), o.cuda())]
+    finally:
+        nat.load().pn_set_option(nat.PN_OPT_PPN_FUSED_TOPK, 1)
+    assert float((imp3 - imp).abs().max()) < 2e-6
+    r3 = torch.topk(imp3.cpu().flatten(1), K).indices
+    for b in (idx3.cpu() != r3).any(1).nonzero().flatten().tolist():
+        r3[b] = torch.from_numpy(stable_topk(imp3[b].flatten().cpu().numpy(), K))
+    assert torch.equal(idx3.cpu(), r3) and torch.equal(sp3.cpu() * N + op3.cpu(), r3)
+
+
+@pytest.mark.parametrize("N", [100, 200, 400])
+def test_pair_topk_fused_adversarial_images_take_the_exact_path(N):
+    """Images the fused kernel cannot threshold (constant / heavily tied / clustered matrices overflow its candidate
+    buffer) are flagged and redone by the exact kernel; results stay bit-exact, ties by ascending flat index."""
+    import torch.nn.functional as F
+    from oracle.head import stable_topk
+    from pairnet_b200 import ops
+    B, K = 16, 100
+    g = torch.Generator().manual_seed(77 + N)
+    s = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    o = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    s[1] = s[1, :1]                      # constant rows: every column of the matrix repeats N times
+    o[1] = o[1, :1]                      # ... and every entry is the same value
+    s[4, :, :] = s[4, :1]                # rank-one: N-fold ties
+    o[7, N // 2:] = o[7, :N - N // 2]    # duplicated objects: pairwise ties
+    o[12] = -o[12, :1]                   # constant columns, negative values
+    imp, idx, sp, op = ops.PpnPlan(B, N, K, "cuda").run_embeds(s.cuda(), o.cuda())
+    torch.cuda.synchronize()
+    ref = torch.matmul(s.double(), o.double().transpose(1, 2))
+    assert float((imp.cpu().double() - ref).abs().max()) < 2e-6
+    for b in range(B):
+        want = torch.from_numpy(stable_topk(imp[b].flatten().cpu().numpy(), K))
+        assert torch.equal(idx[b].cpu(), want), b
+        assert torch.equal(sp[b].cpu() * N + op[b].cpu(), want), b
 
 
 def test_ppn_l2_chunked_batch_equals_unchunked():
