@@ -43,7 +43,7 @@ constexpr int NUM_SPLIT_WARPS = 8;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS + 32 * NUM_SPLIT_WARPS;  // warp0 TMA, warp1 MMA, 2-9 epilogue, 10-17 splitters
 constexpr int LO_SLOTS = 2;
-constexpr int TOPK_MAX = 256, CAND_MAX = 1536;
+constexpr int TOPK_MAX = 256, CAND_MAX = 1408;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int TAIL_PAD = 2048;      // MMA row over-reads past the last tile (< 16 rows >= N: results never stored) stay inside
 
@@ -51,6 +51,7 @@ struct TopkSmem {
   unsigned long long cand[CAND_MAX];
   unsigned long long win[TOPK_MAX];
   uint32_t lm[2 * BM];
+  uint32_t sl[8][32];  // the local maxima as 8 sorted lists
   uint32_t t0;
   unsigned ncand;
 };
@@ -109,6 +110,37 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
 __device__ __forceinline__ float lo_of(float x) {
   const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
   return __uint_as_float(__float_as_uint(x - hi) + 0x1000u);  // + half a TF32 ulp: truncation then rounds to nearest
+}
+
+// Candidates of one 32-column chunk held in v (one matrix row per thread): a 32-bit pass mask is built with two
+// instructions per element; the (rare) passing elements are then fetched by dynamic index from the thread's own row of
+// the swizzled staging tile `srow` (registers cannot be indexed dynamically) and pushed as composites.
+__device__ __forceinline__ void push_candidates(const uint32_t (&v)[32], int nv, float t0f, const uint8_t* srow, int lane,
+                                                uint32_t flat, TopkSmem& tk) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m |= (!(__uint_as_float(v[j]) < t0f)) ? (1u << j) : 0u;  // NaN passes; its key ranks it
+  if (nv < 32) m &= (1u << nv) - 1u;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    const float x = *reinterpret_cast<const float*>(srow + ((((j >> 2) ^ (lane & 7)) << 4) | ((j & 3) << 2)));
+    const unsigned slot = atomicAdd(&tk.ncand, 1u);
+    if (slot < CAND_MAX) tk.cand[slot] = composite(order_key(x), flat + (uint32_t)j);
+  }
+}
+// descending bitonic sort of one key per lane
+__device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+      x = keep_max ? max(x, y) : min(x, y);
+    }
+  }
+  return x;
 }
 
 struct Ring {  // (slot, phase) walker over a ring of runtime depth
@@ -275,14 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
           if (rvalid) {
             const int nv = ncols - c0;  // valid columns of this chunk (>= 32: all)
             if (have_t0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float x = __uint_as_float(v[j]);
-                if (!(x < t0f) && j < nv) {  // NaN passes; the composite key ranks it
-                  const unsigned slot = atomicAdd(&tk.ncand, 1u);
-                  if (slot < CAND_MAX) tk.cand[slot] = composite(order_key(x), flat0 + (uint32_t)(c0 + j));
-                }
-              }
+              push_candidates(v, nv, t0f, sbuf + lane * 128, lane, flat0 + (uint32_t)c0, tk);
             } else if (nv >= 32) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) lm = fmaxf(lm, __uint_as_float(v[j]));
@@ -293,19 +318,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
           }
         }
         if (!have_t0) {
-          // ---- threshold: K-th largest of the 256 local maxima (row x chunk parity) of the image's first tile.  The low
-          // 8 key bits are replaced by the slot number: all entries distinct (one counting pass gives the rank) and the
-          // threshold only moves down by < 256 ulps, so { x >= t0 } still contains the whole top-K.
-          const uint32_t mykey = (order_key(lm) & 0xffffff00u) | (uint32_t)(255 - et);
-          tk.lm[et] = mykey;
+          // ---- threshold: t0 = K-th largest of the 256 local maxima (row x chunk parity) of the image's first tile; they
+          // are distinct matrix elements, so { x >= t0 } contains the whole top-K.  The low 8 key bits are replaced by the
+          // slot number (all entries distinct; t0 only moves down, by < 256 ulps).  The entries are dealt round-robin
+          // to the 8 warps, each sorts its 32 with shuffles, and every thread ranks its entry by binary search in the
+          // other seven sorted lists (an all-pairs count cost 2.5 us per image here, latency bound).
+          tk.lm[et] = (order_key(lm) & 0xffffff00u) | (uint32_t)(255 - et);
           epi_sync();
-          unsigned g0 = 0, g1 = 0, g2 = 0, g3 = 0;
-#pragma unroll 8
-          for (int j = 0; j < 2 * BM; j += 4) {
-            const uint4 m = *reinterpret_cast<const uint4*>(&tk.lm[j]);
-            g0 += m.x > mykey; g1 += m.y > mykey; g2 += m.z > mykey; g3 += m.w > mykey;
+          const int ew = warp - 2;
+          const uint32_t mine = warp_sort_desc(tk.lm[lane * NUM_EPI_WARPS + ew], lane);
+          tk.sl[ew][lane] = mine;
+          epi_sync();
+          {
+            int rank = lane;  // entries of the own list above this one
+#pragma unroll
+            for (int w = 1; w < NUM_EPI_WARPS; ++w) {
+              const uint32_t* l = tk.sl[(ew + w) & (NUM_EPI_WARPS - 1)];
+              int c = 0;  // entries of list l greater than mine
+#pragma unroll
+              for (int st = 16; st > 0; st >>= 1) c += (l[c + st - 1] > mine) ? st : 0;
+              c += l[c] > mine;
+              rank += c;
+            }
+            if (rank == K - 1) tk.t0 = mine & 0xffffff00u;
           }
-          if (g0 + g1 + g2 + g3 == (unsigned)(K - 1)) tk.t0 = mykey & 0xffffff00u;
           epi_sync();
           t0 = tk.t0;
           t0f = key_to_float(t0);
@@ -316,16 +352,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
             for (int c0 = 32 * par; c0 < ncols; c0 += 64) {
               uint32_t v[32];
               tmem_ld_32x32b_x32(tbase + (uint32_t)c0, v);
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile is free again
+              __syncwarp();
               if (rvalid) {
-                const int nv = ncols - c0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float x = __uint_as_float(v[j]);
-                  if (!(x < t0f) && j < nv) {
-                    const unsigned slot = atomicAdd(&tk.ncand, 1u);
-                    if (slot < CAND_MAX) tk.cand[slot] = composite(order_key(x), flat0 + (uint32_t)(c0 + j));
-                  }
-                }
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                push_candidates(v, ncols - c0, t0f, sbuf + lane * 128, lane, flat0 + (uint32_t)c0, tk);
               }
             }
           }
@@ -334,13 +369,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        if (t == tiles_per_img - 1) {
+        const bool last = t == tiles_per_img - 1;
+        if (last || (t & 3) == 0) {
+          // ---- rank the candidates by counting: win[r] = candidate with r larger candidates (the composite order IS the
+          // output order).  Last tile: emit.  Every 4th tile of a multi-tile image: keep the K best so far and raise
+          // t0 to the K-th of them, so that the candidate list stays short however many tiles follow.
           epi_sync();
           const unsigned nc = tk.ncand;
           const bool bad = t0 <= (KEY_NEG_INF | 0xffu) || nc > (unsigned)CAND_MAX || nc < (unsigned)K;
-          if (et == 0) prm.redo[b] = bad ? 1 : 0;
+          if (last && et == 0) prm.redo[b] = bad ? 1 : 0;
           if (!bad) {
-            // ---- rank by counting: win[r] = candidate with r larger candidates
             for (unsigned i = et; i < nc; i += 32 * NUM_EPI_WARPS) {
               const unsigned long long me = tk.cand[i];
               unsigned r0 = 0, r1 = 0;
@@ -354,15 +392,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
               if (r0 + r1 < (unsigned)K) tk.win[r0 + r1] = me;
             }
             epi_sync();
-            for (int r = et; r < K; r += 32 * NUM_EPI_WARPS) {
-              const uint32_t idx = 0xffffffffu - (uint32_t)(tk.win[r] & 0xffffffffull);
-              const size_t o = (size_t)b * K + r;
-              if (prm.topk_idx) prm.topk_idx[o] = (long long)idx;
-              prm.sub_pos[o] = (long long)(idx / (uint32_t)N);
-              prm.obj_pos[o] = (long long)(idx % (uint32_t)N);
+            if (last) {
+              for (int r = et; r < K; r += 32 * NUM_EPI_WARPS) {
+                const uint32_t idx = 0xffffffffu - (uint32_t)(tk.win[r] & 0xffffffffull);
+                const size_t o = (size_t)b * K + r;
+                if (prm.topk_idx) prm.topk_idx[o] = (long long)idx;
+                prm.sub_pos[o] = (long long)(idx / (uint32_t)N);
+                prm.obj_pos[o] = (long long)(idx % (uint32_t)N);
+              }
+            } else {
+              for (int r = et; r < K; r += 32 * NUM_EPI_WARPS) tk.cand[r] = tk.win[r];
+              if (et == 0) tk.ncand = (unsigned)K;
+              t0 = (uint32_t)(tk.win[K - 1] >> 32);
+              t0f = key_to_float(t0);
             }
           }
-          epi_sync();  // smem of this image is recycled by the next one
+          epi_sync();  // last: smem of this image is recycled by the next one; else: the shortened list is published
         }
       }
     }
