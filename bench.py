@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU oracle leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-ppn-microbench", action="store_true", help="skip BASELINE config 5 (PPN only, ~2 s)")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the PyTorch-eager-on-B200 arm (oracle modules on the GPU, ~5 s)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
                     help="keep cuDNN's heuristic algorithm choice for the upstream convolutions (default: autotune per shape "
                          "during warm-up, the reference's `cudnn_benchmark=True` knob of tools/test.py:164-166)")
@@ -342,6 +344,193 @@ def postproc_bench(head, device, with_cpu):
     return out
 
 
+def gpu_eager_baseline(head, mf, mems, device, flush, stream):
+    """PyTorch eager ON THE B200 for the same stages -- the number every hand-written kernel has to
+    beat (the CPU figure is only reported).  The oracle modules (torch restatement of the reference head) are moved to
+    the GPU and timed with CUDA events, L2 flushed between steps, TF32 matmul off (PyTorch's default; what the fp32
+    reference runs) and on.  Baseline leg only: nothing here is on the product path."""
+    import ctypes as C
+    from oracle.head import OCrossHead2
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    torch.manual_seed(10086)
+    o = OCrossHead2().eval()
+    o.init_weights()
+    o = o.to(device)
+    B = mf.shape[0]
+    N = R = 100
+    mf_nchw = mf.contiguous()
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(N, B, 256, generator=g) * 0.5).to(device)          # [N,B,256] last-layer queries
+    pair = (torch.randn(2 * R, B, 256, generator=g) * 0.5).to(device)   # [2K,B,256] pair features
+
+    def ppn_stage():  # pairnet_head.py:322-351 (the MLPs run on all 9 stacked layers there; here on the last one)
+        se = torch.nn.functional.normalize(o.sub_query_update(q).transpose(0, 1), p=2, dim=-1, eps=1e-12)
+        oe = torch.nn.functional.normalize(o.obj_query_update(q).transpose(0, 1), p=2, dim=-1, eps=1e-12)
+        imp = o.update_importance(torch.matmul(se, oe.transpose(1, 2)))
+        idx = torch.topk(imp.flatten(-2, -1), k=R).indices
+        sp, op = torch.div(idx, N, rounding_mode="trunc"), torch.remainder(idx, N)
+        oq = torch.gather(q, 0, op.unsqueeze(-1).repeat(1, 1, 256).transpose(0, 1))
+        sq = torch.gather(q, 0, sp.unsqueeze(-1).repeat(1, 1, 256).transpose(0, 1))
+        return torch.cat([sq, oq], dim=0)
+
+    def rel_stage():  # pairnet_head.py:353-378
+        r = o.rel_query_feat.weight.unsqueeze(1).repeat((1, B, 1))
+        e1 = o.rel_query_embed.weight.unsqueeze(1).repeat((1, B, 1))
+        e2 = o.rel_query_embed2.weight.unsqueeze(1).repeat((1, B, 1))
+        for layer in o.relation_decoder.layers:
+            r = layer(query=r, key=pair, value=pair, query_pos=e1, key_pos=e2)
+        return o.rel_cls_embed(r.transpose(0, 1))
+
+    def timed(fn, n=5):
+        fn()
+        return statistics.mean(time_steps(fn, n, flush, stream))
+
+    out = {"what": "oracle modules (torch restatement of the reference head) .cuda(), eager, CUDA events, L2 flushed",
+           "batch": B}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            out[f"head_{tag}_ms"] = timed(lambda: o.forward_from_memories(mf_nchw, mems), 3)
+            out[f"ppn_stage_{tag}_ms"] = timed(ppn_stage)
+            out[f"relation_fusion_{tag}_ms"] = timed(rel_stage)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    # the same stages through the C-ABI entry points
+    w = head.native_weights()
+    st = stream.cuda_stream
+    qb = q.transpose(0, 1).contiguous()
+    need = lib.pn_ppn_workspace_bytes(B, N, R, 64)
+    ws = torch.empty(need, dtype=torch.uint8, device=device)
+    imp = torch.empty((B, N, N), device=device)
+    sp = torch.empty((B, R), dtype=torch.int64, device=device)
+    op = torch.empty((B, R), dtype=torch.int64, device=device)
+    pf = torch.empty((B, 2 * R, 256), device=device)
+    out["ppn_stage_b200_ms"] = timed(lambda: nat.check(lib.pn_ppn_forward(
+        qb.data_ptr(), None, C.byref(w.sub_query_update), C.byref(w.obj_query_update), C.byref(w.update_importance), None,
+        imp.data_ptr(), None, sp.data_ptr(), op.data_ptr(), pf.data_ptr(), B, N, R, ws.data_ptr(), need, st), "ppn"))
+    need2 = lib.pn_relation_fusion_workspace_bytes(B, R, 2 * R, 2048)
+    ws2 = torch.empty(need2, dtype=torch.uint8, device=device)
+    rel = torch.empty((B, R, 56), device=device)
+    pb = pair.transpose(0, 1).contiguous()
+    out["relation_fusion_b200_ms"] = timed(lambda: nat.check(lib.pn_relation_fusion_forward(
+        C.byref(w.rel), pb.data_ptr(), rel.data_ptr(), None, B, 2 * R, ws2.data_ptr(), need2, st), "rel"))
+    out["head_b200_ms"] = timed(lambda: head.forward_from_memories(mf, mems))
+    out["head_speedup_vs_eager_fp32"] = out["head_fp32_ms"] / out["head_b200_ms"]
+    out["head_speedup_vs_eager_tf32"] = out["head_tf32_ms"] / out["head_b200_ms"]
+    return out
+
+
+def ppn_extras(device, pk, with_cpu):
+    """SURVEY §8d leftovers of config 5: 5a in PyTorch eager on the B200 (cuBLAS bmm + torch.topk), the real-use Bm = 2
+    latency, 5b (ConvTiny between pair matrix and top-k: tensor bound, TFLOP/s), and the CPU timings of the PPN stage."""
+    import torch.nn.functional as F
+    from pairnet_b200 import ops
+    from oracle.head import OConvTiny
+    out = {"eager_5a": [], "latency_bm2": [], "with_convtiny_5b": []}
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    stream = torch.cuda.current_stream()
+    torch.manual_seed(7)
+    conv = OConvTiny().to(device).eval()
+    for N, Bm in ((100, 4096), (200, 2048), (400, 1024)):
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        s = F.normalize(torch.randn(Bm, N, 256, generator=g)).to(device)
+        o = F.normalize(torch.randn(Bm, N, 256, generator=g)).to(device)
+        bytes_per_img = 2 * N * 256 * 4 + N * N * 4 + 2 * 100 * 8
+
+        def eager():
+            imp = torch.matmul(s, o.transpose(1, 2))
+            idx = torch.topk(imp.flatten(-2, -1), k=100).indices
+            return torch.div(idx, N, rounding_mode="trunc"), torch.remainder(idx, N)
+        eager()
+        ms = statistics.mean(time_steps(eager, 5, flush, stream))
+        out["eager_5a"].append({"N": N, "batch": Bm, "ms": ms, "achieved_gbs": Bm * bytes_per_img / (ms * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": Bm * bytes_per_img / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]})
+        # real-use latency: Bm = 2 through the same entry point
+        plan2 = ops.PpnPlan(2, N, 100, device)
+        for _ in range(3):
+            plan2.run_embeds(s[:2], o[:2])
+        ms2 = statistics.mean(time_steps(lambda: plan2.run_embeds(s[:2], o[:2]), 10, flush, stream))
+        eager2 = lambda: torch.topk(torch.matmul(s[:2], o[:2].transpose(1, 2)).flatten(-2, -1), k=100)
+        eager2()
+        out["latency_bm2"].append({"N": N, "b200_us": 1e3 * ms2,
+                                   "eager_us": 1e3 * statistics.mean(time_steps(eager2, 10, flush, stream))})
+        # 5b: ConvTiny between (reference-faithful PPN); 413 952 N^2 flops per image on top of the pair matrix
+        Bc = max(2, Bm // 64)
+        plan = ops.PpnPlan(Bc, N, 100, device)
+        for _ in range(2):
+            plan.run_embeds(s[:Bc], o[:Bc], conv=conv)
+        msc = statistics.mean(time_steps(lambda: plan.run_embeds(s[:Bc], o[:Bc], conv=conv), 5, flush, stream))
+        flops = Bc * (413952.0 * N * N + 2.0 * N * N * 256)
+        def eager_b():
+            with torch.no_grad():
+                return torch.topk(conv(torch.matmul(s[:Bc], o[:Bc].transpose(1, 2))).flatten(-2, -1), k=100)
+        eager_b()
+        mse = statistics.mean(time_steps(eager_b, 3, flush, stream))
+        out["with_convtiny_5b"].append({"N": N, "batch": Bc, "ms": msc, "tflops": flops / (msc * 1e-3) / 1e12,
+                                        "eager_ms": mse, "eager_tflops": flops / (mse * 1e-3) / 1e12})
+    if with_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        convc = OConvTiny().eval()
+        cpu = []
+        for N in (100, 200, 400):
+            for Bm in (2, 64):
+                g = torch.Generator().manual_seed(1234)
+                s = F.normalize(torch.randn(Bm, N, 256, generator=g))
+                o = F.normalize(torch.randn(Bm, N, 256, generator=g))
+                def run(with_conv):
+                    with torch.no_grad():
+                        imp = torch.matmul(s, o.transpose(1, 2))
+                        if with_conv:
+                            imp = convc(imp)
+                        return torch.topk(imp.flatten(-2, -1), k=100)
+                run(False)
+                t0 = time.perf_counter(); run(False); ta = time.perf_counter() - t0
+                if Bm == 2 or N <= 200:
+                    t0 = time.perf_counter(); run(True); tb = time.perf_counter() - t0
+                else:
+                    tb = None  # bounded sample: 64 images of 400x400 through three 7x7 convs takes > 10 s
+                cpu.append({"N": N, "batch": Bm, "pair_topk_ms": 1e3 * ta, "with_convtiny_ms": None if tb is None else 1e3 * tb})
+        out["cpu"] = {"cores": torch.get_num_threads(), "rows": cpu}
+    return out
+
+
+def e2e_simple_test(model, imgs_host, device, flush, stream, steps):
+    """The reference's real inference entry point (tools/test.py -> `PSGTr.simple_test`, psgtr.py:148-156): pinned host
+    images -> backbone -> pixel decoder -> head -> get_bboxes (mask upsampling, panoptic merge) -> triplet2Result ->
+    `Result` objects with every mask on the HOST.  Random-init weights keep no segment, so this times the plumbing of
+    an almost empty result; `postproc` in this line times get_bboxes on confident synthetic head outputs."""
+    B = imgs_host.shape[0]
+    metas = [dict(img_shape=(IMG_H, IMG_W, 3), ori_shape=(IMG_H, IMG_W, 3), batch_input_shape=(IMG_H, IMG_W),
+                  scale_factor=[1.0, 1.0, 1.0, 1.0]) for _ in range(B)]
+    dev_in = torch.empty_like(imgs_host, device=device)
+    nbytes = [0]
+
+    def step():
+        dev_in.copy_(imgs_host, non_blocking=True)
+        res = model.simple_test(dev_in, metas, rescale=False)
+        n = 0
+        for r in res:
+            for v in vars(r).values():
+                if isinstance(v, torch.Tensor):
+                    v = v.cpu()
+                if hasattr(v, "nbytes"):
+                    n += int(v.nbytes)
+                elif isinstance(v, torch.Tensor):
+                    n += v.numel() * v.element_size()
+        nbytes[0] = n
+        stream.synchronize()
+    with torch.no_grad():
+        for _ in range(2):
+            step()
+        ts = time_steps(step, steps, flush, stream)
+    ms = statistics.mean(ts)
+    return {"value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": imgs_host.numel() * imgs_host.element_size(), "d2h_bytes_per_step": nbytes[0],
+            "path": "PSGTr.simple_test -> CrossHead2.simple_test_bboxes/get_bboxes -> triplet2Result (host Result objects)"}
+
+
 def run_b200(args, rank, world, local):
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     device = torch.device("cuda", local)
@@ -387,6 +576,9 @@ def run_b200(args, rank, world, local):
             "pixel_decoder_ms": ev_time(lambda: head.pixel_decoder(feats)),
             "head_cuda_ms": ev_time(lambda: head.forward_from_memories(mf, mems)),
         }
+        eager = None
+        if rank == 0 and world == 1 and not args.no_eager_baseline:
+            eager = gpu_eager_baseline(head, mf, mems, device, flush, stream)
         del feats, mf, mems
 
         # ---- device-resident throughput
@@ -437,6 +629,9 @@ def run_b200(args, rank, world, local):
         post = postproc_bench(head, device, with_cpu=(world == 1 and not args.no_cpu_baseline)) if rank == 0 else None
         roof = dominant_kernel_roofline(model, device, pk) if rank == 0 else None
         micro = ppn_microbench(device, pk) if (rank == 0 and not args.no_ppn_microbench) else None
+        extras = (ppn_extras(device, pk, with_cpu=not args.no_cpu_baseline)
+                  if (rank == 0 and world == 1 and not args.no_ppn_microbench) else None)
+        e2e_st = e2e_simple_test(model, imgs_host, device, flush, stream, min(args.steps, 10)) if rank == 0 else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -455,7 +650,9 @@ def run_b200(args, rank, world, local):
                    "l2_flush": "256 MiB read+write between timed steps (outside the event pair)",
                    "cuda_graph": not args.no_graph, "cudnn_benchmark": not args.no_cudnn_benchmark,
                    "upstream": "ResNet-50 and the pixel decoder's 1x1/3x3 convs on cuDNN (TF32 conv default, as PyTorch); "
-                               "deformable encoder, GroupNorm, FPN merge and mask_feature conv hand-written (3xTF32 / fp32)"},
+                               "deformable encoder, GroupNorm, FPN merge and mask_feature conv hand-written (3xTF32 / fp32)",
+                   "precision_note": "the fp32 label holds for the hand-written head (3xTF32 / FFMA, fp32-level accuracy); "
+                                     "the upstream cuDNN convolutions run single-pass TF32"},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
                 "result": "all_cls_scores (sub,obj,cls,rel,importance) + sub_pos/obj_pos to pinned host; mask tensors stay on device"},
@@ -469,6 +666,12 @@ def run_b200(args, rank, world, local):
     }
     if micro is not None:
         line["ppn_microbench"] = micro
+    if extras is not None:
+        line["ppn_extras"] = extras
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+    if e2e_st is not None:
+        line["e2e_simple_test"] = e2e_st
     if post is not None:
         line["postproc"] = post
     print(json.dumps(line), flush=True)

@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(256) conv3_kernel(const float* __restrict__ x,
 size_t conv_tiny_workspace_bytes(int B, int N, int mid) {
   size_t act = ((size_t)B * mid * N * N * sizeof(float) + 255) & ~size_t(255);
   size_t wp = ((size_t)mid * mid * 49 * sizeof(float) + 255) & ~size_t(255);
-  return 2 * act + wp;
+  const size_t ffma = 2 * act + wp;
+  const size_t tc = mid == 64 ? conv_tiny_tc_workspace_bytes(B, N) : 0;  // conv_umma.cu
+  return ffma > tc ? ffma : tc;
 }
 
 template <int C>
@@ -213,6 +215,9 @@ int launch_conv_tiny(const float* x, const PnConvTiny* cv, float* y, int B, int 
   for (int i = 0; i < 3; ++i) PN_REQUIRE(cv->w[i] && cv->b[i], PN_ERR_BAD_ARG, "conv_tiny: null weights");
   Workspace ws(wsp, ws_bytes);
   PN_REQUIRE(wsp, PN_ERR_WORKSPACE, "conv_tiny: null workspace");
+  // conv2 (98 % of the flops) as a tcgen05 implicit GEMM (conv_umma.cu); PN_OPT_CONV_TC = 0 keeps the FFMA kernels
+  if (cv->mid_channels == 64 && get_option(OPT_TENSOR_CORES) && get_option(OPT_CONV_TC))
+    return launch_conv_tiny_tc(x, cv, y, B, N, wsp, ws_bytes, st);
   if (cv->mid_channels == 64) return conv_tiny_impl<64>(x, cv, y, B, N, ws, st);
   if (cv->mid_channels == 16) return conv_tiny_impl<16>(x, cv, y, B, N, ws, st);
   set_error("conv_tiny: mid_channels=%d (supported: 16, 64)", cv->mid_channels);

@@ -262,6 +262,34 @@ def test_conv_tiny_against_reference_golden():
         assert rel_err(got, g["out"]) < 1e-5, tag
 
 
+@pytest.mark.parametrize("B,N", [(2, 100), (3, 37), (1, 130), (2, 200), (5, 16), (1, 8)])
+def test_conv_tiny_tcgen05_matches_fp64_and_ffma(B, N):
+    """conv2 as a tcgen05 implicit GEMM (shifted-window descriptors over zero-padded TMA slabs, 3xTF32) against the
+    fp64 convolution of the same module and against the exact-fp32 FFMA kernels; ragged patches and image edges."""
+    from oracle.head import OConvTiny
+    from pairnet_b200 import _native as nat, ops
+    torch.manual_seed(40 + N)
+    m = OConvTiny(mid_channels=64)
+    x = torch.tanh(_t((B, N, N), 300 + N))
+    with torch.no_grad():
+        ref = m.double()(x.double())
+    m = m.float().cuda()
+    lib = nat.load()
+    assert lib.pn_get_option(nat.PN_OPT_CONV_TC) == 1
+    got = ops.conv_tiny(x.cuda(), m).cpu()
+    lib.pn_set_option(nat.PN_OPT_CONV_TC, 0)
+    try:
+        ffma = ops.conv_tiny(x.cuda(), m).cpu()
+    finally:
+        lib.pn_set_option(nat.PN_OPT_CONV_TC, 1)
+    scale = float(ref.abs().max())
+    print(f"conv_tiny B={B} N={N}: tcgen05 {float((got.double() - ref).abs().max()) / scale:.2e}  "
+          f"ffma {float((ffma.double() - ref).abs().max()) / scale:.2e} (max abs err / max |ref|, vs fp64)")
+    assert float((ffma.double() - ref).abs().max()) < 1e-5 * scale
+    assert float((got.double() - ref).abs().max()) < 1e-5 * scale
+    assert float((got - ffma).abs().max()) < 1e-5 * scale
+
+
 @pytest.mark.parametrize("N,K", [(100, 100), (200, 100), (37, 5), (100, 1), (64, 1024), (400, 100)])
 def test_topk_pairs_bit_exact(N, K):
     from pairnet_b200 import ops
