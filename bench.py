@@ -458,7 +458,7 @@ def ppn_extras(device, pk, with_cpu):
                                    "eager_us": 1e3 * statistics.mean(time_steps(eager2, 10, flush, stream))})
         # 5b: ConvTiny between (reference-faithful PPN); 413 952 N^2 flops per image on top of the pair matrix
         Bc = max(2, Bm // 64)
-        plan = ops.PpnPlan(Bc, N, 100, device)
+        plan = ops.PpnPlan(Bc, N, 100, device, mid_channels=64)
         for _ in range(2):
             plan.run_embeds(s[:Bc], o[:Bc], conv=conv)
         msc = statistics.mean(time_steps(lambda: plan.run_embeds(s[:Bc], o[:Bc], conv=conv), 5, flush, stream))
@@ -466,10 +466,19 @@ def ppn_extras(device, pk, with_cpu):
         def eager_b():
             with torch.no_grad():
                 return torch.topk(conv(torch.matmul(s[:Bc], o[:Bc].transpose(1, 2))).flatten(-2, -1), k=100)
-        eager_b()
-        mse = statistics.mean(time_steps(eager_b, 3, flush, stream))
-        out["with_convtiny_5b"].append({"N": N, "batch": Bc, "ms": msc, "tflops": flops / (msc * 1e-3) / 1e12,
-                                        "eager_ms": mse, "eager_tflops": flops / (mse * 1e-3) / 1e12})
+        row = {"N": N, "batch": Bc, "ms": msc, "tflops": flops / (msc * 1e-3) / 1e12,
+               "arithmetic": "3xTF32 on tcgen05, fp32 parity (1.6e-6 of the output scale vs fp64)"}
+        prev = torch.backends.cudnn.allow_tf32
+        try:
+            for tag, tf32 in (("eager_cudnn_tf32", True), ("eager_cudnn_fp32", False)):
+                torch.backends.cudnn.allow_tf32 = tf32  # PyTorch's default is True: single-pass TF32, NOT fp32 parity
+                eager_b()
+                mse = statistics.mean(time_steps(eager_b, 3, flush, stream))
+                row[tag + "_ms"] = mse
+                row[tag + "_tflops"] = flops / (mse * 1e-3) / 1e12
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        out["with_convtiny_5b"].append(row)
     if with_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
         convc = OConvTiny().eval()

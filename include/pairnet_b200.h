@@ -238,6 +238,7 @@ PN_API int pn_m2f_decoder_forward(const PnM2FWeights* w, const PnM2FInputs* in, 
  * conv == NULL selects the "pair matrix + top-k only" microbenchmark mode (BASELINE config 5a).
  * sub_mlp == NULL: `query` is taken as already-normalised sub embeddings and `query_obj` as obj
  * embeddings (microbenchmark inputs); otherwise query_obj must be NULL. */
+/* mid_channels <= 0: workspace of the ConvTiny-less microbenchmark mode (conv == NULL) only. */
 PN_API size_t pn_ppn_workspace_bytes(int B, int N, int K, int mid_channels);
 PN_API int pn_ppn_forward(const float* query, const float* query_obj, const PnMlp3* sub_mlp,
                    const PnMlp3* obj_mlp, const PnConvTiny* conv,

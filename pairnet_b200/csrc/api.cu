@@ -656,7 +656,7 @@ static size_t ppn_bytes(int B, int N, int K, int mid) {
   const int M = B * N;
   for (int i = 0; i < 4; ++i) ws.take<float>((size_t)2 * M * D);
   ws.take<float>((size_t)B * N * N);
-  ws.take<char>(conv_tiny_workspace_bytes(B, N, mid > 0 ? mid : 64));
+  if (mid > 0) ws.take<char>(conv_tiny_workspace_bytes(B, N, mid));  // mid_channels <= 0: no ConvTiny (config 5a)
   ws.take<int>((size_t)B);
   return ws.off + 1024;
 }

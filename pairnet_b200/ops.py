@@ -186,8 +186,10 @@ def topk_pairs(importance, K, query=None):
 class PpnPlan:
     """Pre-allocated buffers for repeated ``pn_ppn_forward`` calls (micro-benchmark 5a/5b)."""
 
-    def __init__(self, B, N, K, device, mid_channels=64):
+    def __init__(self, B, N, K, device, mid_channels=0):
+        """mid_channels = 0: pair matrix + top-k only (5a); 64: workspace for ``run_embeds(..., conv=...)`` as well."""
         lib = nat.load()
+        self.mid_channels = mid_channels
         self.B, self.N, self.K = B, N, K
         self.need = lib.pn_ppn_workspace_bytes(B, N, K, mid_channels)
         self.ws = torch.empty(self.need, dtype=torch.uint8, device=device)
@@ -200,6 +202,8 @@ class PpnPlan:
         """microbench mode: already-normalised embeddings -> pair matrix (-> conv) -> top-k."""
         cvp, keep = (None, None)
         if conv is not None:
+            if self.mid_channels <= 0:
+                raise ValueError("PpnPlan was sized without ConvTiny workspace (pass mid_channels=64)")
             cv, keep = _conv_struct(conv)
             cvp = C.byref(cv)
         nat.check(nat.load().pn_ppn_forward(sub_embed.data_ptr(), obj_embed.data_ptr(), None, None, cvp,
