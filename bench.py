@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~20 s CPU oracle leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-ppn-microbench", action="store_true", help="skip BASELINE config 5 (PPN only, ~2 s)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (config 3 shape, ~10 s)")
     ap.add_argument("--no-eager-baseline", action="store_true",
                     help="skip the PyTorch-eager-on-B200 arm (oracle modules on the GPU, ~5 s)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
@@ -540,6 +541,46 @@ def e2e_simple_test(model, imgs_host, device, flush, stream, steps):
             "path": "PSGTr.simple_test -> CrossHead2.simple_test_bboxes/get_bboxes -> triplet2Result (host Result objects)"}
 
 
+def train_bench(device, rank, world, steps):
+    """BASELINE config 3 shape at fp32: one data-parallel TRAINING step per rank on bs = 2 synthetic 800x1333 images with
+    synthetic targets (12 masks, 10 triplets per image): forward (backbone / pixel decoder on the no-grad CUDA path, head
+    differentiable on the device), Hungarian targets + losses, backward, bucketed NCCL gradient all-reduce launched
+    from autograd hooks, grad clip, AdamW.  The backward is PyTorch autograd (no hand-written backward kernels yet)."""
+    from pairnet_b200.trainer import TrainStep, synthetic_targets
+    out = {}
+    metas = [dict(img_shape=(IMG_H, IMG_W, 3), batch_input_shape=(IMG_H, IMG_W)) for _ in range(PER_GPU_BATCH)]
+    imgs = synthetic_images(PER_GPU_BATCH, 20000 + rank).to(device)
+    rels, labels, masks = synthetic_targets(PER_GPU_BATCH, (IMG_H, IMG_W), 10086 + rank, device)
+    for scope in ("relation", "head"):
+        model = build_model(device)           # identical weights on every rank (seed 10086)
+        ts = TrainStep(model, scope=scope)
+        torch.manual_seed(1234 + rank)        # sample points / dropout streams
+        losses = None
+        for _ in range(3):
+            losses = ts(imgs, metas, rels, labels, masks)
+        torch.cuda.synchronize()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            losses = ts(imgs, metas, rels, labels, masks)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world, device) / steps
+        out[scope] = {"ms_per_step": ms, "images_per_sec": world * PER_GPU_BATCH / (ms * 1e-3), "steps": steps,
+                      "trainable_params": ts.num_params, "allreduce_bytes_per_step": ts.reducer.bytes if world > 1 else 0,
+                      "allreduce_buckets": len(ts.reducer.buckets), "collectives_per_step": ts.collectives,
+                      "losses_last_step": {k: float(v.detach()) for k, v in losses.items()}}
+        ts.reducer.close()
+        del ts, model
+        torch.cuda.empty_cache()
+    out["what"] = ("fp32 training step, bs=2/GPU, frozen backbone + pixel decoder (no-grad CUDA path); scope 'relation' = "
+                   "Pair-Net side trains on the CUDA library's decoder output, scope 'head' = everything after the pixel "
+                   "decoder trains; gradients all-reduced over NCCL in 25 MB buckets overlapped with backward")
+    return out
+
+
 def run_b200(args, rank, world, local):
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     device = torch.device("cuda", local)
@@ -642,6 +683,11 @@ def run_b200(args, rank, world, local):
                   if (rank == 0 and world == 1 and not args.no_ppn_microbench) else None)
         e2e_st = e2e_simple_test(model, imgs_host, device, flush, stream, min(args.steps, 10)) if rank == 0 else None
 
+    train = None
+    if not args.no_train:
+        del runner
+        torch.cuda.empty_cache()
+        train = train_bench(device, rank, world, steps=min(args.steps, 10))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = time_cpu_oracle(steps=3, warmup=1, images_per_step=1, budget_s=30.0)
@@ -681,6 +727,8 @@ def run_b200(args, rank, world, local):
         line["gpu_eager_baseline"] = eager
     if e2e_st is not None:
         line["e2e_simple_test"] = e2e_st
+    if train is not None:
+        line["train_step"] = train
     if post is not None:
         line["postproc"] = post
     print(json.dumps(line), flush=True)

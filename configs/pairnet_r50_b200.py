@@ -57,7 +57,16 @@ model = dict(
         loss_mask=dict(type="CrossEntropyLoss", use_sigmoid=True, reduction="mean", loss_weight=5.0),
         loss_dice=dict(type="DiceLoss", use_sigmoid=True, activate=True, reduction="mean", naive_dice=True, eps=1.0,
                        loss_weight=5.0)),
-    train_cfg=None,
+    # configs/mask2former/pairnet.py:190-207
+    train_cfg=dict(
+        id_assigner=dict(type="IdMatcher", sub_id_cost=dict(type="ClassificationCost", weight=1.0),
+                         obj_id_cost=dict(type="ClassificationCost", weight=1.0),
+                         r_cls_cost=dict(type="ClassificationCost", weight=0.0)),
+        num_points=12544, oversample_ratio=3.0, importance_sample_ratio=0.75,
+        mask_assigner=dict(type="MaskHungarianAssigner", cls_cost=dict(type="ClassificationCost", weight=2.0),
+                           mask_cost=dict(type="CrossEntropyLossCost", weight=5.0, use_sigmoid=True),
+                           dice_cost=dict(type="DiceCost", weight=5.0, pred_act=True, eps=1.0)),
+        sampler=dict(type="MaskPseudoSampler")),
     test_cfg=dict(max_per_img=100),
 )
 

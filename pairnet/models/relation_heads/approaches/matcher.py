@@ -1,12 +1,3 @@
-"""Import target of ``custom_imports`` (reference ``approaches/matcher.py``).  The Hungarian triplet
-matcher is training-only; registered as a config-holding placeholder."""
-from pairnet_b200.registry import BBOX_ASSIGNERS
-
-
-@BBOX_ASSIGNERS.register_module()
-class IdMatcher:
-    def __init__(self, **cfg):
-        self.cfg = cfg
-
-    def assign(self, *a, **k):
-        raise NotImplementedError("IdMatcher.assign: training targets are SURVEY §8f rank 2 (not built yet)")
+"""Import target of ``custom_imports`` (reference ``approaches/matcher.py``): the Hungarian triplet matcher the config
+names (``configs/mask2former/pairnet.py:191-196``) lives in ``pairnet_b200/training.py``."""
+from pairnet_b200.training import IdMatcher  # noqa: F401

@@ -40,7 +40,24 @@ class PSGTr(nn.Module):
 
     def forward_train(self, img, img_metas, gt_rels=None, gt_bboxes=None, gt_labels=None, gt_masks=None,
                       gt_bboxes_ignore=None):
-        raise NotImplementedError("training (psgtr.py:112-146) depends on SURVEY §8f rank 2 (targets + losses)")
+        """psgtr.py:112-146.  ``gt_masks``: per image a ``[G,h,w]`` tensor (or an object with mmdet ``BitmapMasks``'
+        ``to_ndarray()``); padded to the batch shape and resized to half resolution with nearest sampling."""
+        import torch.nn.functional as F
+        with torch.no_grad():   # the backbone (and the pixel decoder inside the head) stay on the no-grad path
+            x = self.extract_feat(img)
+        if self.bbox_head.use_mask:
+            assert gt_masks is not None
+            _, _, H, W = img.shape
+            new_gt_masks = []
+            for each in gt_masks:
+                mask = each if torch.is_tensor(each) else torch.as_tensor(each.to_ndarray())
+                mask = mask.to(x[0].device)
+                _, h, w = mask.shape
+                mask = F.interpolate(F.pad(mask, (0, W - w, 0, H - h)).unsqueeze(1).float(), size=(H // 2, W // 2),
+                                     mode="nearest").squeeze(1).to(mask.dtype)
+                new_gt_masks.append(mask)
+            gt_masks = new_gt_masks
+        return self.bbox_head.forward_train(x, img_metas, gt_rels, gt_bboxes, gt_labels, gt_masks, gt_bboxes_ignore)
 
     def simple_test(self, img, img_metas, rescale=False):
         """psgtr.py:148-156: head post-processing -> one ``Result`` per image."""

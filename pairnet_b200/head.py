@@ -15,6 +15,7 @@ import torch.nn as nn
 from . import _native as nat
 from .registry import (HEADS, ConfigDict, build_loss, build_plugin_layer, build_positional_encoding,
                        build_transformer_layer_sequence, to_config)
+from .training import TrainMixin
 
 
 class ConvTiny(nn.Module):
@@ -57,7 +58,7 @@ INSTANCE_OFFSET = 1000  # mmdet.datasets.coco_panoptic.INSTANCE_OFFSET (pairnet_
 
 
 @HEADS.register_module()
-class CrossHead2(nn.Module):
+class CrossHead2(TrainMixin, nn.Module):
     def __init__(self, num_classes, in_channels, num_relations, num_obj_query=100, num_rel_query=100,
                  mapper="conv_tiny", use_mask=True, pixel_decoder=None, transformer_decoder=None, feat_channels=256,
                  out_channels=256, num_transformer_feat_level=3, embed_dims=256, relation_decoder=None,
@@ -128,6 +129,8 @@ class CrossHead2(nn.Module):
         self.mask_embed = _mlp3(feat_channels)
         self.test_cfg = test_cfg
         self.train_cfg = train_cfg
+        self._init_train_cfg(train_cfg)   # assigners / sampler / num_points (pairnet_head.py:129-137)
+        self.train_scope = "head"         # which parameters receive gradients in forward_train (torch_head.py)
         self.num_obj_query = num_obj_query
         self.in_channels = in_channels
         self.loss_cfgs = dict(loss_cls=loss_cls, loss_mask=loss_mask, loss_dice=loss_dice, rel_cls_loss=rel_cls_loss,
@@ -162,8 +165,38 @@ class CrossHead2(nn.Module):
         mask_features, memorys = self.pixel_decoder(feats)
         return self.forward_from_memories(mask_features, memorys)
 
-    def forward_train(self, *args, **kwargs):
-        raise NotImplementedError("training targets/losses (pairnet_head.py:419-757) are SURVEY §8f rank 2, not built yet")
+    def train_outputs(self, feats, img_metas=None, scope=None):
+        """Head outputs WITH autograd history for the training step.  The pixel decoder (and the backbone before it) run
+        on the no-grad CUDA / cuDNN path; ``scope="relation"`` additionally runs the Mask2Former decoder through the CUDA
+        library (no gradients) and differentiates only the Pair-Net side; ``scope="head"`` differentiates everything
+        after the pixel decoder (PyTorch ops on the device, ``torch_head.py``)."""
+        from . import torch_head as th
+        scope = scope or self.train_scope
+        with torch.no_grad():
+            mask_features, memorys = self.pixel_decoder(feats)
+        if scope == "relation":
+            taps = {}
+            cls_scores, mask_preds = self.forward_from_memories(mask_features, memorys, taps=taps, materialize_seg=False)
+            query_feat = taps["query_out"].transpose(0, 1).contiguous()      # [N,B,256], last decoder layer
+            return th.relation_side(self, query_feat, cls_scores["cls"], mask_preds["mask"])[:2]
+        if scope != "head":
+            raise ValueError(f"train scope {scope!r}: 'relation' or 'head'")
+        mask_features = mask_features.float().contiguous()
+        query_feat, cls_pred, mask_pred = th.masked_decoder(self, mask_features, [m.float().contiguous() for m in memorys])
+        return th.relation_side(self, query_feat, cls_pred, mask_pred)[:2]
+
+    def forward_train(self, x, img_metas, gt_rels, gt_bboxes, gt_labels=None, gt_masks=None, gt_bboxes_ignore=None,
+                      proposal_cfg=None, **kwargs):
+        """pairnet_head.py:720-757 -> dict(loss_r_cls, loss_sub_cls, loss_obj_cls, loss_match)."""
+        assert proposal_cfg is None, '"proposal_cfg" must be None'
+        if self.train_cfg is None:
+            raise RuntimeError("CrossHead2 was built without train_cfg (assigners / sampler): cannot train")
+        outs = self.train_outputs(x, img_metas)
+        if gt_labels is None:
+            loss_inputs = outs + (gt_rels, gt_bboxes, gt_masks, img_metas)
+        else:
+            loss_inputs = outs + (gt_rels, gt_bboxes, gt_labels, gt_masks, img_metas)
+        return self.loss(*loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)
 
     # ------------------------------------------------------------------ inference post-processing (pairnet_head.py:759-930)
     def simple_test_bboxes(self, feats, img_metas, rescale=False):

@@ -55,3 +55,53 @@ def test_reference_arm_nonzero_rank_exits_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import torch.nn as nn
+    from pairnet_b200.trainer import GradReducer
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                     # identical replicas
+    net = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 4))
+    params = list(net.parameters())
+    red = GradReducer(params, bucket_bytes=300)              # three small buckets
+    opt = torch.optim.SGD(params, lr=0.1)
+    x = torch.full((3, 8), float(rank + 1))                  # per-rank data
+    for step in range(2):
+        net(x).square().sum().backward()
+        n = red.finish()
+        assert n == len(red.buckets) and n >= 3              # every bucket was reduced from its hook
+        opt.step()
+        red.zero_grad()
+    # the same two steps on the concatenated batch, single process, mean of the per-rank gradients
+    torch.manual_seed(0)
+    ref = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 16), nn.ReLU(), nn.Linear(16, 4))
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for step in range(2):
+        ropt.zero_grad()
+        sum(ref(torch.full((3, 8), float(r + 1))).square().sum() for r in range(world)).div(world).backward()
+        ropt.step()
+    err = max(float((a - b).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+    q.put((rank, err, [float(p.sum()) for p in net.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_gloo():
+    """GradReducer (trainer.py): gradients accumulate into flat buckets, each bucket is all-reduced from the autograd
+    hook of its last parameter, replicas stay identical and equal the single-process large-batch step."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] < 1e-6 and res[1][1] < 1e-6
+    assert res[0][2] == res[1][2]                             # replicas bit-identical after the reduced steps

@@ -69,7 +69,9 @@ def oracle_small_head(seed=10086, dtype=torch.float32):
 def product_head_cfg():
     from pairnet_b200.registry import Config
     cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_r50_b200.py"), import_custom_modules=False)
-    return cfg.model.bbox_head
+    head = cfg.model.bbox_head
+    head["train_cfg"] = cfg.model.get("train_cfg")   # mmdet SingleStageDetector.__init__ injects it into the head
+    return head
 
 
 def product_small_head(oracle_head, device="cuda"):
