@@ -189,5 +189,10 @@ def test_detector_forward_dispatch_mirrors_mmdet_base_detector():
         m(img, metas, return_loss=False)            # not wrapped in augmentation lists
     with pytest.raises(NotImplementedError):
         m([img, img], [metas, metas], return_loss=False)   # aug_test
-    with pytest.raises(NotImplementedError):
-        m(img, metas, return_loss=True)             # training: SURVEY 8f rank 2
+    class TrainStub(Stub):
+        def forward_train(self, img, img_metas, **kw):
+            calls.append(("forward_train", tuple(img.shape), sorted(kw)))
+            return dict(loss_match=0.0)
+    t = TrainStub()
+    assert t(img, metas, return_loss=True, gt_rels=[], gt_labels=[], gt_masks=[]) == dict(loss_match=0.0)
+    assert calls[-1] == ("forward_train", (2, 3, 8, 12), ["gt_labels", "gt_masks", "gt_rels"])   # training: SURVEY 8f-2
