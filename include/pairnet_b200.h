@@ -100,6 +100,8 @@ PN_API int pn_get_option(int key);
                                     once and never read back; 0 = pair-matrix kernel followed by the stand-alone top-k kernel */
 #define PN_OPT_CONV_TC 12       /* default 1: ConvTiny conv2 (64 -> 64, 7x7) as a tcgen05 implicit GEMM (3xTF32, shifted-window A
                                     descriptors over TMA-loaded slabs, conv_umma.cu); 0 = FFMA kernels of ppn.cu */
+#define PN_OPT_UMMA_TMA_STORE 13 /* default 1: row-major epilogue of the tcgen05 GEMM through swizzled staging tiles + TMA stores
+                                    (0 = one 128-bit store per thread and row: measured store-issue bound) */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

@@ -18,6 +18,11 @@ constexpr int BM = 128, BK = 32;            // BK fp32 = 128 B = one SWIZZLE_128
 constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
 // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each takes half the columns)
 constexpr int BIAS_MAX = 1024;              // per-problem bias staged in smem (epilogue reads it with LDS, not LDG)
+// TMA-store epilogue: one swizzled 32-row x 32-column fp32 staging tile per epilogue warp (4 warps).  A thread-per-row
+// STG touches 32 lines per instruction (~6.5 cycles per 16-byte request): the ncu role profile showed the four
+// epilogue warps 100 % busy and every other role waiting on them -- the kernel was store-issue bound, not MMA bound.
+constexpr int EPI_TILE_BYTES = 32 * 128;
+constexpr int EPI_STAGE_BYTES = 4 * EPI_TILE_BYTES;
 // BN = 128: 3 stages x 64 KiB, 2 x 128 TMEM columns.  BN = 256 (N % 256 == 0): A tiles are re-read half as often;
 // 2 stages x 96 KiB, 2 x 256 TMEM columns (the whole TMEM).
 template <int BN>
@@ -27,14 +32,17 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // a_hi, a_lo, b_hi, b_lo
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr size_t SMEM_BYTES =
-      (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BIAS_MAX * sizeof(float);
+      (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + EPI_STAGE_BYTES + 256 /*barriers*/ + 4 * BIAS_MAX * sizeof(float);
 };
 
 // raw-A variant: 4 stages x (A raw 16 KiB + B hi/lo 32 KiB)
-constexpr size_t RAW_SMEM_BYTES = (size_t)4 * (A_TILE_BYTES + 2 * 128 * BK * 4) + 1024 + 256 + 4 * BIAS_MAX * sizeof(float);
+constexpr size_t RAW_SMEM_BYTES =
+    (size_t)4 * (A_TILE_BYTES + 2 * 128 * BK * 4) + 1024 + EPI_STAGE_BYTES + 256 + 4 * BIAS_MAX * sizeof(float);
 
 struct Problem {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;  // A [M,K], W [N,K]; box 32 x 128, SWIZZLE_128B
+  CUtensorMap c_map, clo_map;          // C / C_lo [M,N] (row pitch ldc); box 32 x 32: TMA-store epilogue
+  int tma_store;                       // row-major store through the staging tile + TMA (else per-thread STG)
   const float* bias;
   float* C;
   float* C_lo;  // non-null: write the result pre-split for a following 3xTF32 GEMM (C = hi, C_lo = lo)
@@ -94,11 +102,13 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES;
   constexpr int OFF_B_HI = A_RAW ? A_TILE_BYTES : 2 * A_TILE_BYTES;
   constexpr int OFF_B_LO = OFF_B_HI + B_TILE;
+  constexpr bool TMA_EPI = (NUM_EPI_WARPS == 4 && BN == 128);
   constexpr int TM_A = 2 * BN;  // A_RAW: TMEM columns [TM_A + set*64, +32) = hi, [+32, +64) = lo  (4 sets -> 512 total)
   static_assert(!A_RAW || BN == 128, "raw-A variant is built for 128x128 tiles");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // [4 warps][32 rows x 128 B], 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
@@ -106,7 +116,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   uint64_t* a_ready_bar = tmem_empty_bar + 2;     // [ASETS]  splitter -> MMA   (A_RAW)
   uint64_t* a_free_bar = a_ready_bar + ASETS;     // [ASETS]  MMA -> splitter   (A_RAW)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_free_bar + ASETS);
-  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
+  float* bias_s = reinterpret_cast<float*>(epi_stage + EPI_STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const bool is_epi = warp >= 2 && warp < 2 + NUM_EPI_WARPS;
@@ -320,6 +330,57 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
               }
             }
           }
+        } else if (TMA_EPI && P.tma_store) {
+          // row-major store through this warp's swizzled staging tile: ONE TMA store per 32 x 32 block (rows >= M and
+          // columns >= N are clipped by the tensor map); the hi/lo split store sends two tiles
+          if (tc.m0 + quad * 32 >= P.M || n0 + c0 >= P.N) continue;  // warp-uniform
+          uint8_t* sb = epi_stage + (size_t)(warp - 2) * EPI_TILE_BYTES;
+          float o[32];
+          if (P.bias_per_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + bias_row;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + j);
+              o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+            }
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          const uint32_t sb_row = smem_u32(sb) + lane * 128;
+          const uint32_t xr = (uint32_t)(lane & 7);
+          auto store_tile = [&](const float (&t)[32], const CUtensorMap* map) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile's previous store
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb_row + (((uint32_t)j ^ xr) << 4)),
+                           "f"(t[4 * j]), "f"(t[4 * j + 1]), "f"(t[4 * j + 2]), "f"(t[4 * j + 3])
+                           : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                           "r"(smem_u32(sb)), "r"(n0 + c0), "r"(tc.m0 + quad * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          };
+          if (!P.C_lo) {
+            store_tile(o, &P.c_map);
+          } else {
+            float h[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = rna_tf32(o[j]);
+            store_tile(h, &P.c_map);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = rna_tf32(o[j] - h[j]);
+            store_tile(h, &P.clo_map);
+          }
         } else if (row < P.M && n0 + c0 < P.N) {
           float* dst = P.C + (size_t)row * P.ldc + n0 + c0;
           float* dlo = P.C_lo ? P.C_lo + (size_t)row * P.ldc + n0 + c0 : nullptr;
@@ -359,6 +420,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // outstanding TMA stores (smem + global)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (A_RAW) {
     // ===== A splitter: raw fp32 tile (smem, SWIZZLE_128B) -> hi / lo in tensor memory, one row per thread
@@ -383,9 +445,12 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
           const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float h = rna_tf32(x[u]);
-            hi[c * 4 + u] = __float_as_uint(h);
-            lo[c * 4 + u] = __float_as_uint(rna_tf32(x[u] - h));
+            // rna_tf32 in two integer ops: round to nearest, ties away from zero == add half an ulp to the magnitude and
+            // clear the low 13 bits (cvt.rna.tf32.f32 compiles to ~9 instructions with its NaN / Inf selects); the lo
+            // part only gets the half-ulp nudge, the tensor pipe's own truncation does the rest
+            const uint32_t h = (__float_as_uint(x[u]) + 0x1000u) & 0xffffe000u;
+            hi[c * 4 + u] = h;
+            lo[c * 4 + u] = __float_as_uint(x[u] - __uint_as_float(h)) + 0x1000u;
           }
         }
         tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64, hi);
@@ -528,6 +593,12 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     PN_TRY(make_map(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
     PN_TRY(make_map(&p.a_lo, (passes == 3 && !o.a_is_raw) ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
     PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
+    p.tma_store = 0;
+    if (!o.bits && o.t_rows <= 0 && get_option(OPT_UMMA_TMA_STORE) && o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0) {
+      PN_TRY(make_tmap_2d(&p.c_map, o.C, o.M, o.N, o.ldc, 32, 32));
+      if (o.C_lo) PN_TRY(make_tmap_2d(&p.clo_map, o.C_lo, o.M, o.N, o.ldc, 32, 32));
+      p.tma_store = 1;
+    }
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
     p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
     p.bits = o.bits; p.rowany = o.rowany; p.bits_words = o.bits_words;

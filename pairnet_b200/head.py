@@ -57,6 +57,19 @@ def _ptr(t):
 INSTANCE_OFFSET = 1000  # mmdet.datasets.coco_panoptic.INSTANCE_OFFSET (pairnet_head.py:16)
 
 
+def attach_native(module):
+    """INTEGRATION.md Option B: give ANY module that carries the reference ``CrossHead2``'s attribute names (the
+    reference class itself inside an mmdet environment) the B200 forward.  Binds the native plumbing of this file's
+    ``CrossHead2`` to ``module`` and creates the four cache slots; afterwards
+    ``module.forward_from_memories(mask_features, multi_scale_memorys)`` is the hot path."""
+    import types
+    for name in ("_hot_params", "_mlp", "_layer", "native_weights", "_pos_table", "forward_from_memories"):
+        setattr(module, name, types.MethodType(getattr(CrossHead2, name), module))
+    module._lin, module._norm = CrossHead2._lin, CrossHead2._norm      # static helpers
+    module._wkey, module._wstruct, module._pos_cache, module._ws = None, None, {}, None
+    return module
+
+
 @HEADS.register_module()
 class CrossHead2(TrainMixin, nn.Module):
     def __init__(self, num_classes, in_channels, num_relations, num_obj_query=100, num_rel_query=100,
@@ -344,7 +357,7 @@ class CrossHead2(TrainMixin, nn.Module):
         self._mlp(w.sub_query_update, self.sub_query_update)
         self._mlp(w.obj_query_update, self.obj_query_update)
         cv = w.update_importance
-        cv.mid_channels = self.update_importance.mid_channels
+        cv.mid_channels = self.update_importance.conv_layers[0][0].out_channels
         for i in range(3):
             conv = self.update_importance.conv_layers[i][0]
             cv.w[i], cv.b[i] = _ptr(conv.weight), _ptr(conv.bias)

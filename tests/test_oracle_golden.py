@@ -109,3 +109,35 @@ def test_stable_topk_contract():
     rng = np.random.default_rng(0)
     x = rng.standard_normal(1000).astype(np.float32)
     assert stable_topk(x, 50).tolist() == torch.topk(torch.from_numpy(x), 50).indices.tolist()
+
+
+def test_attach_native_on_the_reference_class_if_present():
+    """INTEGRATION.md Option B on the reference's OWN CrossHead2 (built over the oracle's mmcv shims): ``attach_native``
+    finds every attribute the native plumbing reads -- the struct fill runs through until the first device requirement
+    (CPU parameters -> NativeError), never an AttributeError."""
+    if not os.path.isdir("/root/reference/pairnet"):
+        pytest.skip("reference tree not present on this box")
+    import subprocess
+    import sys
+    from tests.util import ROOT
+    code = (
+        "import torch\n"
+        "from oracle import pin_reference as pr\n"
+        "from pairnet_b200.head import attach_native\n"
+        "from pairnet_b200 import _native as nat\n"
+        "h = attach_native(pr.build_reference_head())\n"
+        "ps = h._hot_params()\n"
+        "assert len(ps) > 250 and h._wkey is None and h._pos_cache == {}\n"
+        "try:\n"
+        "    h.native_weights()\n"
+        "    raise SystemExit('expected NativeError on CPU parameters')\n"
+        "except nat.NativeError as e:\n"
+        "    assert 'CUDA' in str(e)\n"
+        "try:\n"
+        "    h.forward_from_memories(torch.zeros(1, 256, 8, 8), [torch.zeros(1, 256, 2, 2)] * 3)\n"
+        "    raise SystemExit('expected NativeError on CPU tensors')\n"
+        "except nat.NativeError:\n"
+        "    pass\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
