@@ -541,6 +541,32 @@ def e2e_simple_test(model, imgs_host, device, flush, stream, steps):
             "path": "PSGTr.simple_test -> CrossHead2.simple_test_bboxes/get_bboxes -> triplet2Result (host Result objects)"}
 
 
+def config4_head_bench(device, flush, stream):
+    """BASELINE config 4's HEAD shapes (200 object / 200 relation queries, 1024x1024 input -> mask_features 256x256,
+    memories 32^2 / 64^2 / 128^2, one image per GPU): the hot path alone on synthetic pixel-decoder outputs, in the
+    fp32-parity arithmetic of config 2 (3xTF32) -- the Swin-L backbone and a bf16 arithmetic path are not built, so this
+    is the extrapolated config's head only, labelled as such."""
+    from pairnet_b200.registry import Config, build_head
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_r50_b200.py"), import_custom_modules=False).model.bbox_head
+    cfg["pixel_decoder"] = None
+    cfg["num_obj_query"] = cfg["num_rel_query"] = 200
+    torch.manual_seed(10086)
+    head = build_head(cfg)
+    head.init_weights()
+    head = head.to(device).eval()
+    g = torch.Generator().manual_seed(4)
+    mf = (torch.randn(1, 256, 256, 256, generator=g) * 0.5).to(device).contiguous(memory_format=torch.channels_last)
+    mems = [torch.randn(1, 256, s, s, generator=g).to(device) for s in (32, 64, 128)]
+    with torch.no_grad():
+        for _ in range(3):
+            head.forward_from_memories(mf, mems)
+        ms = statistics.mean(time_steps(lambda: head.forward_from_memories(mf, mems), 10, flush, stream))
+    return {"what": "CrossHead2 hot path at BASELINE config 4's head shapes: 200/200 queries, 1024x1024 input "
+                    "(mask_features 256x256; 1 024 / 4 096 / 16 384 memory tokens), 1 image per GPU, eager launches",
+            "ms_per_image": ms, "images_per_sec_per_gpu": 1e3 / ms, "launches": head.last_launch_count,
+            "dtype": "fp32 (3xTF32); bf16 path and Swin-L backbone not built -> extrapolated config, head only"}
+
+
 def train_bench(device, rank, world, steps):
     """BASELINE config 3 shape at fp32: one data-parallel TRAINING step per rank on bs = 2 synthetic 800x1333 images with
     synthetic targets (12 masks, 10 triplets per image): forward (backbone / pixel decoder on the no-grad CUDA path, head
@@ -682,6 +708,7 @@ def run_b200(args, rank, world, local):
         extras = (ppn_extras(device, pk, with_cpu=not args.no_cpu_baseline)
                   if (rank == 0 and world == 1 and not args.no_ppn_microbench) else None)
         e2e_st = e2e_simple_test(model, imgs_host, device, flush, stream, min(args.steps, 10)) if rank == 0 else None
+        cfg4 = config4_head_bench(device, flush, stream) if (rank == 0 and not args.no_ppn_microbench) else None
 
     train = None
     if not args.no_train:
@@ -729,6 +756,8 @@ def run_b200(args, rank, world, local):
         line["e2e_simple_test"] = e2e_st
     if train is not None:
         line["train_step"] = train
+    if cfg4 is not None:
+        line["config4_head"] = cfg4
     if post is not None:
         line["postproc"] = post
     print(json.dumps(line), flush=True)

@@ -210,9 +210,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
         for (int j = 0; j < 32; ++j) {
           const float p = ((w[c] >> j) & 1u) ? 0.f : fast_exp2(__uint_as_float(v[j]) - m_new);
           lsum += p;
-          const float hi = rna_tf32(p);
-          ph[j] = __float_as_uint(hi);
-          pl[j] = __float_as_uint(rna_tf32(p - hi));
+          // truncation-hi split (see pair_topk.cu): the tensor pipe ignores the low 13 mantissa bits, so p itself is the
+          // hi operand; lo = p - trunc(p), nudged by half a TF32 ulp so that the hardware truncation rounds it to
+          // nearest.  3 instructions per element instead of ~18 for two cvt.rna.tf32 (this loop is the kernel's
+          // critical path: the ncu role profile shows the softmax warps 88 % busy, MMA and TMA waiting on them)
+          ph[j] = __float_as_uint(p);
+          pl[j] = __float_as_uint(p - __uint_as_float(__float_as_uint(p) & 0xffffe000u)) + 0x1000u;
         }
         tmem_st_32x32b_x32(tmem + lane_addr + TM_PHI + c * 32, ph);
         tmem_st_32x32b_x32(tmem + lane_addr + TM_PLO + c * 32, pl);
