@@ -316,9 +316,12 @@ typedef struct {
 typedef struct {
   int num_layers, num_levels, num_points, ffn_dims;
   PnMsdaEncoderLayer layers[PN_MAX_LAYERS];
+  const void* prepared; /* NULL, or the blob filled by pn_msda_encoder_prepare (static TF32 weight splits) */
 } PnMsdaEncoderWeights;
 /* x_in/x_out [B,nq,256] token-major (levels concatenated, low -> high res order of `h`,`w`);
  * pos [nq,256] = sine position + level encoding.  Linears run on the tcgen05 3xTF32 GEMM. */
+PN_API size_t pn_msda_encoder_prepared_bytes(const PnMsdaEncoderWeights* w);
+PN_API int pn_msda_encoder_prepare(const PnMsdaEncoderWeights* w, void* blob, size_t blob_bytes, pn_stream_t stream);
 PN_API size_t pn_msda_encoder_workspace_bytes(int B, int nq, int ffn_dims, int num_levels, int num_points);
 PN_API int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, const float* pos,
                                    const int* h, const int* w_, float* x_out, int B, void* ws, size_t ws_bytes,

@@ -87,7 +87,7 @@ class PnMsdaEncoderLayer(C.Structure):
 
 class PnMsdaEncoderWeights(C.Structure):
     _fields_ = [("num_layers", C.c_int), ("num_levels", C.c_int), ("num_points", C.c_int), ("ffn_dims", C.c_int),
-                ("layers", PnMsdaEncoderLayer * PN_MAX_LAYERS)]
+                ("layers", PnMsdaEncoderLayer * PN_MAX_LAYERS), ("prepared", c_void_p)]
 
 
 i32, i64, sz, vp = C.c_int, C.c_longlong, C.c_size_t, c_void_p
@@ -144,6 +144,8 @@ SIGNATURES = {
     "pn_gather_rows": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "pn_upsample_threshold": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "pn_panoptic_merge": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_longlong, vp, vp, vp]),
+    "pn_msda_encoder_prepared_bytes": (sz, [P(PnMsdaEncoderWeights)]),
+    "pn_msda_encoder_prepare": (i32, [P(PnMsdaEncoderWeights), vp, sz, vp]),
     "pn_msda_encoder_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
     "pn_msda_encoder_forward": (i32, [P(PnMsdaEncoderWeights), vp, vp, P(i32), P(i32), vp, i32, vp, sz, vp]),
     "pn_group_norm_workspace_bytes": (sz, [i32, i32, i32]),

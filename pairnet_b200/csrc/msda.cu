@@ -21,10 +21,8 @@ struct MsdaGeom {
   int nq;                         // tokens per image
 };
 
-__device__ __forceinline__ float rna_tf32m(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
+__device__ __forceinline__ float rna_tf32m(float v) {  // == cvt.rna.tf32.f32 for finite inputs, 2 integer ops (umma_ptx.cuh)
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 
 // value [B,nq,256] ; ol [B*nq, ldo]: cols [0, 8*L*P*2) offsets ((h,l,p),xy), then 8*L*P attention logits ((h),(l,p))
@@ -193,11 +191,57 @@ static void enc_take(Workspace& ws, EncBuffers& b, size_t M, int ffn, int ldo) {
   b.b_ol = ws.take<float>(ldo);
 }
 
+
+static inline size_t enc_wmax(int ffn, int ldo) { return (size_t)D * D * 2 + (size_t)ldo * D + (size_t)2 * ffn * D; }
+static inline size_t enc_layer_floats(int ffn, int ldo) { return 2 * enc_wmax(ffn, ldo) + (size_t)round_up(ldo, 64); }
+// TF32 hi/lo splits of one layer's six weight matrices + the concatenated [offsets ; attention] bias
+static int enc_prepare_layer(const PnMsdaEncoderLayer& Lw, float* w_hi, float* w_lo, float* b_ol, int ffn, int ldo,
+                             int n_off, int n_att, cudaStream_t st) {
+  float* wo_hi = w_hi + (size_t)D * D;            float* wo_lo = w_lo + (size_t)D * D;
+  float* wp_hi = wo_hi + (size_t)ldo * D;         float* wp_lo = wo_lo + (size_t)ldo * D;
+  float* w1_hi = wp_hi + (size_t)D * D;           float* w1_lo = wp_lo + (size_t)D * D;
+  float* w2_hi = w1_hi + (size_t)ffn * D;         float* w2_lo = w1_lo + (size_t)ffn * D;
+  PN_TRY(launch_split_tf32(Lw.value_proj.w, w_hi, w_lo, (size_t)D * D, st));
+  PN_TRY(launch_split_tf32(Lw.sampling_offsets.w, wo_hi, wo_lo, (size_t)n_off * D, st));
+  PN_TRY(launch_split_tf32(Lw.attention_weights.w, wo_hi + (size_t)n_off * D, wo_lo + (size_t)n_off * D, (size_t)n_att * D,
+                           st));
+  PN_TRY(launch_split_tf32(Lw.output_proj.w, wp_hi, wp_lo, (size_t)D * D, st));
+  PN_TRY(launch_split_tf32(Lw.ffn1.w, w1_hi, w1_lo, (size_t)ffn * D, st));
+  PN_TRY(launch_split_tf32(Lw.ffn2.w, w2_hi, w2_lo, (size_t)ffn * D, st));
+  cudaError_t e = cudaMemcpyAsync(b_ol, Lw.sampling_offsets.b, sizeof(float) * n_off, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(b_ol + n_off, Lw.attention_weights.b, sizeof(float) * n_att, cudaMemcpyDeviceToDevice, st);
+  PN_REQUIRE(e == cudaSuccess, (int)e, "msda_encoder: memcpy: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 }  // namespace pn
 
 using namespace pn;
 
 extern "C" {
+
+size_t pn_msda_encoder_prepared_bytes(const PnMsdaEncoderWeights* w) {
+  if (!w || w->num_layers < 1 || w->num_layers > PN_MAX_LAYERS) return 0;
+  const int ldo = (int)round_up(NH * w->num_levels * w->num_points * 3, 4);
+  return (size_t)w->num_layers * enc_layer_floats(w->ffn_dims, ldo) * sizeof(float) + 256;
+}
+
+/* builds the static operands of the encoder's tcgen05 GEMMs once per weight version; set w->prepared = blob afterwards */
+int pn_msda_encoder_prepare(const PnMsdaEncoderWeights* w, void* blob, size_t blob_bytes, pn_stream_t stream) {
+  PN_REQUIRE(w && blob && blob_bytes >= pn_msda_encoder_prepared_bytes(w) && ((uintptr_t)blob & 255) == 0, PN_ERR_BAD_ARG,
+             "msda_encoder_prepare: bad blob");
+  const int ffn = w->ffn_dims;
+  const int LP = w->num_levels * w->num_points;
+  const int n_off = NH * LP * 2, n_att = NH * LP;
+  const int ldo = (int)round_up(n_off + n_att, 4);
+  for (int i = 0; i < w->num_layers; ++i) {
+    float* base = reinterpret_cast<float*>(blob) + (size_t)i * enc_layer_floats(ffn, ldo);
+    PN_TRY(enc_prepare_layer(w->layers[i], base, base + enc_wmax(ffn, ldo), base + 2 * enc_wmax(ffn, ldo), ffn, ldo, n_off,
+                             n_att, as_stream(stream)));
+  }
+  return 0;
+}
 
 size_t pn_msda_encoder_workspace_bytes(int B, int nq, int ffn_dims, int num_levels, int num_points) {
   Workspace ws(nullptr, 0);
@@ -232,11 +276,6 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
   PN_REQUIRE(ws.ok(), PN_ERR_WORKSPACE, "msda_encoder: workspace too small (%zu needed, %zu given)", ws.off, ws.cap);
 
   const int Mi = (int)M;
-  auto memcpy_d2d = [&](void* d, const void* s, size_t bytes) -> int {
-    cudaError_t e = cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st);
-    PN_REQUIRE(e == cudaSuccess, (int)e, "msda_encoder: memcpy: %s", cudaGetErrorString(e));
-    return 0;
-  };
   // raw mode: activations enter the tcgen05 GEMM as plain fp32 and are split inside the SM (TMEM), so no
   // producer materialises hi/lo copies; otherwise every producer emits its output pre-split.
   const bool raw = get_option(OPT_UMMA_RAW_A) != 0;
@@ -251,23 +290,24 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
   for (int i = 0; i < w->num_layers; ++i) {
     const PnMsdaEncoderLayer& Lw = w->layers[i];
     // split this layer's weights: [value_proj | sampling_offsets ; attention_weights | output_proj | ffn1 | ffn2]
-    float* wv_hi = b.w_hi;                          float* wv_lo = b.w_lo;
+    // this layer's split weights [value_proj | sampling_offsets ; attention_weights | output_proj | ffn1 | ffn2] and
+    // concatenated offset / attention biases: from the prepared blob (static: built once by pn_msda_encoder_prepare)
+    // or, without one, split into the workspace on every call (6 launches + 2 copies per layer)
+    float *w_hi_l = b.w_hi, *w_lo_l = b.w_lo, *b_ol_l = b.b_ol;
+    if (w->prepared) {
+      float* base = reinterpret_cast<float*>(const_cast<void*>(w->prepared)) + (size_t)i * enc_layer_floats(ffn, ldo);
+      w_hi_l = base; w_lo_l = base + enc_wmax(ffn, ldo); b_ol_l = base + 2 * enc_wmax(ffn, ldo);
+    } else {
+      PN_TRY(enc_prepare_layer(Lw, w_hi_l, w_lo_l, b_ol_l, ffn, ldo, n_off, n_att, st));
+    }
+    float* wv_hi = w_hi_l;                          float* wv_lo = w_lo_l;
     float* wo_hi = wv_hi + (size_t)D * D;           float* wo_lo = wv_lo + (size_t)D * D;
     float* wp_hi = wo_hi + (size_t)ldo * D;         float* wp_lo = wo_lo + (size_t)ldo * D;
     float* w1_hi = wp_hi + (size_t)D * D;           float* w1_lo = wp_lo + (size_t)D * D;
     float* w2_hi = w1_hi + (size_t)ffn * D;         float* w2_lo = w1_lo + (size_t)ffn * D;
-    PN_TRY(launch_split_tf32(Lw.value_proj.w, wv_hi, wv_lo, (size_t)D * D, st));
-    PN_TRY(launch_split_tf32(Lw.sampling_offsets.w, wo_hi, wo_lo, (size_t)n_off * D, st));
-    PN_TRY(launch_split_tf32(Lw.attention_weights.w, wo_hi + (size_t)n_off * D, wo_lo + (size_t)n_off * D,
-                             (size_t)n_att * D, st));
-    PN_TRY(launch_split_tf32(Lw.output_proj.w, wp_hi, wp_lo, (size_t)D * D, st));
-    PN_TRY(launch_split_tf32(Lw.ffn1.w, w1_hi, w1_lo, (size_t)ffn * D, st));
-    PN_TRY(launch_split_tf32(Lw.ffn2.w, w2_hi, w2_lo, (size_t)ffn * D, st));
-    PN_TRY(memcpy_d2d(b.b_ol, Lw.sampling_offsets.b, sizeof(float) * n_off));
-    PN_TRY(memcpy_d2d(b.b_ol + n_off, Lw.attention_weights.b, sizeof(float) * n_att));
     {  // value = x Wv^T + bv ; ol = q [Wo;Wa]^T + [bo;ba]
       UmmaOperand o[2] = {{b.x_hi, b.x_lo, D, wv_hi, wv_lo, D, Lw.value_proj.b, b.value, D, Mi, D, D},
-                          {b.q_hi, b.q_lo, D, wo_hi, wo_lo, D, b.b_ol, b.ol, ldo, Mi, n_ol, D}};
+                          {b.q_hi, b.q_lo, D, wo_hi, wo_lo, D, b_ol_l, b.ol, ldo, Mi, n_ol, D}};
       if (raw) {
         o[0].a_hi = x_cur; o[0].a_lo = nullptr; o[0].a_is_raw = 1;
         o[1].a_hi = q_raw; o[1].a_lo = nullptr; o[1].a_is_raw = 1;

@@ -6,10 +6,8 @@
 
 namespace pn {
 
-__device__ __forceinline__ float rna_tf32f(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
+__device__ __forceinline__ float rna_tf32f(float v) {  // == cvt.rna.tf32.f32 for finite inputs, 2 integer ops (umma_ptx.cuh)
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

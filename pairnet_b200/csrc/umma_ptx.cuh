@@ -108,10 +108,11 @@ __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return d;
 }
 
+// round to nearest TF32, ties away from zero -- what cvt.rna.tf32.f32 computes -- as two integer ops: add half a TF32 ulp
+// to the magnitude bits, clear the low 13.  ptxas expands the cvt into ~9 instructions (NaN / Inf selects); this
+// form is bit-identical for every finite input and Inf, and keeps quiet NaNs NaN.
 __device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 

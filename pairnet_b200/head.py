@@ -334,7 +334,7 @@ class CrossHead2(TrainMixin, nn.Module):
     def native_weights(self):
         """``PnHeadWeights`` over the current parameter storage (rebuilt when any pointer changes)."""
         params = self._hot_params()
-        key = tuple(p.data_ptr() for p in params)
+        key = tuple((p.data_ptr(), p._version) for p in params)   # in-place updates (optimizer steps) invalidate the prepared splits
         if key == self._wkey:
             return self._wstruct
         for p in params:

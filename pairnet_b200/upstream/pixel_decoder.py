@@ -199,7 +199,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
 
     def _native_weights(self):
         params = list(self.encoder.parameters())
-        key = tuple(p.data_ptr() for p in params)
+        key = tuple((p.data_ptr(), p._version) for p in params)   # in-place updates (optimizer steps) invalidate the prepared splits
         if key == self._enc_key:
             return self._enc_struct
         w = nat.PnMsdaEncoderWeights()
@@ -221,6 +221,15 @@ class MSDeformAttnPixelDecoder(nn.Module):
             lin(d.ffn2, layer.ffns[0].layers[1])
             for j in range(2):
                 d.norm[j].gamma, d.norm[j].beta = layer.norms[j].weight.data_ptr(), layer.norms[j].bias.data_ptr()
+        # static TF32 weight splits + concatenated biases of the six layers: built once per weight version
+        lib = nat.load()
+        dev = params[0].device
+        if dev.type == "cuda":
+            need = lib.pn_msda_encoder_prepared_bytes(C.byref(w))
+            self._enc_blob = torch.empty(need, dtype=torch.uint8, device=dev)
+            nat.check(lib.pn_msda_encoder_prepare(C.byref(w), self._enc_blob.data_ptr(), need,
+                                                  torch.cuda.current_stream(dev).cuda_stream), "pn_msda_encoder_prepare")
+            w.prepared = self._enc_blob.data_ptr()
         self._enc_key, self._enc_struct = key, w
         return w
 

@@ -63,3 +63,20 @@ def test_training_steps_update_exactly_the_trainable_set(scope):
     assert hist[-1] < hist[0]                                  # the same batch six times: the trained losses go down
     assert float(model.bbox_head.rel_cls_loss.cum_samples.sum()) > 0
     ts.reducer.close()
+
+
+def test_inference_after_training_uses_the_updated_weights():
+    """The CUDA library caches TF32 splits of the weights (prepared blobs); an optimizer step updates the parameters in
+    place, so the cache key carries the tensors' version counters."""
+    head = product_small_head(oracle_small_head())
+    from oracle.make_golden import small_head_inputs
+    mf, mems = small_head_inputs(1, (16, 24), 31)
+    mf, mems = mf.cuda(), [m.cuda() for m in mems]
+    a, _ = head.forward_from_memories(mf, mems)
+    a = {k: v.clone() for k, v in a.items()}
+    with torch.no_grad():
+        head.rel_cls_embed.weight.mul_(1.5)
+        head.relation_decoder.layers[0].ffns[0].layers[1].weight.add_(0.01)
+    b, _ = head.forward_from_memories(mf, mems)
+    assert not torch.allclose(a["rel"], b["rel"])
+    assert torch.equal(a["cls"], b["cls"])
