@@ -259,11 +259,11 @@ def dominant_kernel_roofline(model, device, pk):
     ms_ffma = statistics.mean(time_steps(launch_ffma, 5, flush, torch.cuda.current_stream()))
     alg_bytes = 4.0 * (M * d + 2 * 2 * d * d + M * 2 * d)  # A (raw fp32), W hi+lo, C
     return {"bound": "tensor", "kernel": "umma_gemm_kernel<128,4,raw-A>: tcgen05.mma kind::tf32 x3 (fp32-parity hi/lo split, A "
-                                         "split in-SM through TMEM), K/V-projection problem of the 100x167 level, "
-                                         "M=33400 N=512 K=256",
+                                         "split in-SM through TMEM, TMA-store epilogue), K/V-projection problem of the "
+                                         "100x167 level, M=33400 N=512 K=256",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": 52.79e6, "traffic_source": "ncu --set full r01g capture (profiles/r01g_tcgen05_kernels_ncu.md): "
-                                                  "dram read 35.35 MB + write 17.43 MB per launch",
+            "traffic": 47.6e6, "traffic_source": "ncu --set full r02l capture (profiles/r02l_ncu_metrics.md, umma_gemm_kv): "
+                                                  "dram read + write 47.6 MB per launch (C partly still in L2 at kernel end)",
             "algorithmic_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": flops, "tensor_pipe_flops_per_launch": 3 * flops,
             "peak_source": pk["source"], "ffma_kernel_ms_same_problem": ms_ffma,
