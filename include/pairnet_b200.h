@@ -102,6 +102,10 @@ PN_API int pn_get_option(int key);
                                     descriptors over TMA-loaded slabs, conv_umma.cu); 0 = FFMA kernels of ppn.cu */
 #define PN_OPT_UMMA_TMA_STORE 13 /* default 1: row-major epilogue of the tcgen05 GEMM through swizzled staging tiles + TMA stores
                                     (0 = one 128-bit store per thread and row: measured store-issue bound) */
+#define PN_OPT_SINGLE_PASS 14    /* default 0 = fp32 parity (3xTF32).  1 = reduced-precision mode for the bf16-class configs: the
+                                    memory-side tcgen05 GEMMs (K/V projections, mask einsums, pixel-decoder encoder) and the masked
+                                    cross-attention run ONE kind::tf32 pass on the raw fp32 operands (10-bit mantissa >= bf16's 8);
+                                    the pair matrix, ConvTiny and the top-k stay at fp32 parity */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

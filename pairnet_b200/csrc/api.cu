@@ -11,7 +11,7 @@ namespace pn {
 
 static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 void set_error(const char* fmt, ...) {

@@ -42,6 +42,7 @@ struct Params {
   float2* ml;      // [S,B,NH,Nq]
   int B, Nq, Nk, splits, tiles_per_split;
   int k_col0, vt_img_rows, vt_row0;
+  int passes;  // 3 = 3xTF32 (fp32 parity); 1 = single-pass TF32 (PN_OPT_SINGLE_PASS): hi operands only
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_constant__ Params prm) {
@@ -88,10 +89,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
 
   if (warp == 0) {
     // warp-uniform loop, one elected lane issues the TMA (see elect_one)
+    const bool three = prm.passes == 3;
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * TILE16K);
+      mbar_expect_tx(q_full, three ? 2 * TILE16K : TILE16K);
       tma_load_2d(q_hi_s, &prm.q_hi, q_full, h * HD, b * prm.Nq + qt * TQ);
-      tma_load_2d(q_lo_s, &prm.q_lo, q_full, h * HD, b * prm.Nq + qt * TQ);
+      if (three) tma_load_2d(q_lo_s, &prm.q_lo, q_full, h * HD, b * prm.Nq + qt * TQ);
     }
     __syncwarp();
     for (int t = 0; t < ntiles; ++t) {
@@ -101,13 +103,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
       uint8_t* st = stage0 + (size_t)s * STAGE_BYTES;
       const int key0 = (tile0 + t) * TKEYS;
       if (elect_one()) {
-        mbar_expect_tx(&kv_full[s], STAGE_BYTES);
+        mbar_expect_tx(&kv_full[s], three ? STAGE_BYTES : STAGE_BYTES / 2);
         tma_load_2d(st, &prm.k_hi, &kv_full[s], prm.k_col0 + h * HD, b * prm.Nk + key0);
-        tma_load_2d(st + TILE16K, &prm.k_lo, &kv_full[s], prm.k_col0 + h * HD, b * prm.Nk + key0);
+        if (three) tma_load_2d(st + TILE16K, &prm.k_lo, &kv_full[s], prm.k_col0 + h * HD, b * prm.Nk + key0);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           tma_load_2d(st + 2 * TILE16K + a * VT_ATOM, &prm.vt_hi, &kv_full[s], key0 + a * 32, b * prm.vt_img_rows + prm.vt_row0 + h * HD);
-          tma_load_2d(st + 3 * TILE16K + a * VT_ATOM, &prm.vt_lo, &kv_full[s], key0 + a * 32, b * prm.vt_img_rows + prm.vt_row0 + h * HD);
+          if (three)
+            tma_load_2d(st + 3 * TILE16K + a * VT_ATOM, &prm.vt_lo, &kv_full[s], key0 + a * 32, b * prm.vt_img_rows + prm.vt_row0 + h * HD);
         }
       }
       __syncwarp();
@@ -128,9 +131,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < HD / UMMA_K; ++k) {
           const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-          umma_tf32(tmem + TM_S, dq_lo + koff, dk_hi + koff, idesc_s, k == 0 ? 0u : 1u);
-          umma_tf32(tmem + TM_S, dq_hi + koff, dk_lo + koff, idesc_s, 1u);
-          umma_tf32(tmem + TM_S, dq_hi + koff, dk_hi + koff, idesc_s, 1u);
+          if (prm.passes == 3) {
+            umma_tf32(tmem + TM_S, dq_lo + koff, dk_hi + koff, idesc_s, k == 0 ? 0u : 1u);
+            umma_tf32(tmem + TM_S, dq_hi + koff, dk_lo + koff, idesc_s, 1u);
+            umma_tf32(tmem + TM_S, dq_hi + koff, dk_hi + koff, idesc_s, 1u);
+          } else {
+            umma_tf32(tmem + TM_S, dq_hi + koff, dk_hi + koff, idesc_s, k == 0 ? 0u : 1u);
+          }
         }
         umma_commit(s_full);
       }
@@ -146,9 +153,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
             const uint64_t dv_hi = make_smem_desc(st + 2 * TILE16K + a * VT_ATOM) + koff;
             const uint64_t dv_lo = make_smem_desc(st + 3 * TILE16K + a * VT_ATOM) + koff;
-            umma_tf32_ts(tmem + TM_O, tmem + TM_PLO + col, dv_hi, idesc_o, (a == 0 && k == 0) ? 0u : 1u);
-            umma_tf32_ts(tmem + TM_O, tmem + TM_PHI + col, dv_lo, idesc_o, 1u);
-            umma_tf32_ts(tmem + TM_O, tmem + TM_PHI + col, dv_hi, idesc_o, 1u);
+            if (prm.passes == 3) {
+              umma_tf32_ts(tmem + TM_O, tmem + TM_PLO + col, dv_hi, idesc_o, (a == 0 && k == 0) ? 0u : 1u);
+              umma_tf32_ts(tmem + TM_O, tmem + TM_PHI + col, dv_lo, idesc_o, 1u);
+              umma_tf32_ts(tmem + TM_O, tmem + TM_PHI + col, dv_hi, idesc_o, 1u);
+            } else {
+              umma_tf32_ts(tmem + TM_O, tmem + TM_PHI + col, dv_hi, idesc_o, (a == 0 && k == 0) ? 0u : 1u);
+            }
           }
         }
         umma_commit(o_full);
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fa_umma_kernel(const __grid_co
           pl[j] = __float_as_uint(p - __uint_as_float(__float_as_uint(p) & 0xffffe000u)) + 0x1000u;
         }
         tmem_st_32x32b_x32(tmem + lane_addr + TM_PHI + c * 32, ph);
-        tmem_st_32x32b_x32(tmem + lane_addr + TM_PLO + c * 32, pl);
+        if (prm.passes == 3) tmem_st_32x32b_x32(tmem + lane_addr + TM_PLO + c * 32, pl);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -293,6 +304,7 @@ int launch_fa_umma(const FaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) 
   prm.k_col0 = a.k_col0; prm.vt_img_rows = vt_img_rows; prm.vt_row0 = a.vt_row0;
   prm.mask_bits = a.mask_bits; prm.mask_words = a.mask_words; prm.rowany = a.rowany;
   prm.out = a.out; prm.B = a.B; prm.Nq = a.Nq; prm.Nk = a.Nk;
+  prm.passes = get_option(OPT_SINGLE_PASS) ? 1 : 3;
   const int qtiles = cdiv(a.Nq, TQ);
   const int base = a.B * NH * qtiles;
   const int total_tiles = cdiv(a.Nk, TKEYS);

@@ -575,6 +575,10 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   using namespace umma;
   PN_REQUIRE(count >= 1 && count <= MAX_PROBLEMS, PN_ERR_BAD_ARG, "umma: bad problem count");
   PN_REQUIRE(passes == 1 || passes == 3, PN_ERR_BAD_ARG, "umma: passes must be 1 or 3");
+  // PN_OPT_SINGLE_PASS: reduced-precision mode -- every tensor-core GEMM runs ONE kind::tf32 pass on the raw fp32
+  // operands (the tensor pipe truncates them to TF32: 10-bit mantissa, >= bf16's 8); no hi/lo planes are read or written
+  const bool single = get_option(OPT_SINGLE_PASS) != 0;
+  if (single) passes = 1;
   Params prm{};
   prm.passes = passes;
   int maxM = 0, maxN = 0;
@@ -582,7 +586,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     const UmmaOperand& o = ops[i];
     PN_REQUIRE(o.a_hi && o.w_hi && (o.C || o.bits) && (passes == 1 || ((o.a_lo || o.a_is_raw) && o.w_lo)), PN_ERR_BAD_ARG,
                "umma: null operand");
-    PN_REQUIRE(!o.a_is_raw || passes == 3, PN_ERR_BAD_ARG, "umma: raw A operands need passes == 3");
+    PN_REQUIRE(!o.a_is_raw || passes == 3 || single, PN_ERR_BAD_ARG, "umma: raw A operands need passes == 3");
     PN_REQUIRE(o.K % BK == 0 && o.K >= BK, PN_ERR_UNSUPPORTED, "umma: K=%d must be a multiple of %d", o.K, BK);
     PN_REQUIRE(o.bias_per_row || cdiv(o.N, 256) * 256 <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: N=%d exceeds %d", o.N,
                BIAS_MAX);
@@ -596,15 +600,15 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     p.tma_store = 0;
     if (!o.bits && o.t_rows <= 0 && get_option(OPT_UMMA_TMA_STORE) && o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0) {
       PN_TRY(make_tmap_2d(&p.c_map, o.C, o.M, o.N, o.ldc, 32, 32));
-      if (o.C_lo) PN_TRY(make_tmap_2d(&p.clo_map, o.C_lo, o.M, o.N, o.ldc, 32, 32));
+      if (o.C_lo && !single) PN_TRY(make_tmap_2d(&p.clo_map, o.C_lo, o.M, o.N, o.ldc, 32, 32));
       p.tma_store = 1;
     }
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
-    p.C_lo = o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
+    p.C_lo = single ? nullptr : o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
     p.bits = o.bits; p.rowany = o.rowany; p.bits_words = o.bits_words;
     PN_REQUIRE(!o.bits || (o.rowany && o.bits_words > 0), PN_ERR_BAD_ARG, "umma: bit-pack epilogue needs rowany/words");
     PN_REQUIRE(!o.bias_per_row || o.M <= BIAS_MAX, PN_ERR_UNSUPPORTED, "umma: per-row bias needs M <= %d", BIAS_MAX);
-    PN_REQUIRE(!o.C_lo || ((uintptr_t)o.C_lo & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C_lo must be 16B aligned");
+    PN_REQUIRE(single || !o.C_lo || ((uintptr_t)o.C_lo & 15) == 0, PN_ERR_UNSUPPORTED, "umma: C_lo must be 16B aligned");
     maxM = o.M > maxM ? o.M : maxM;
     maxN = o.N > maxN ? o.N : maxN;
   }
