@@ -289,8 +289,19 @@ def ppn_microbench(device, pk):
         ms = statistics.mean(ts)
         bytes_per_img = 2 * N * 256 * 4 + N * N * 4 + 2 * 100 * 8
         gbs = Bm * bytes_per_img / (ms * 1e-3) / 1e9
-        out.append({"N": N, "batch": Bm, "ms": ms, "algorithmic_bytes_per_image": bytes_per_img, "achieved_gbs": gbs,
-                    "frac_of_hbm_peak": gbs / pk["hbm_gbs"]})
+        row = {"N": N, "batch": Bm, "ms": ms, "algorithmic_bytes_per_image": bytes_per_img, "achieved_gbs": gbs,
+               "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "images_per_sec": Bm / (ms * 1e-3)}
+        # bf16 run ("fp32 (and a bf16 run)"): bf16 embeddings through pn_ppn_pair_topk_bf16, fp32
+        # matrix and int64 indices out; the algorithmic bytes shrink with the operand type
+        sb, ob = s.to(torch.bfloat16), o.to(torch.bfloat16)
+        for _ in range(3):
+            plan.run_embeds_bf16(sb, ob)
+        ms16 = statistics.mean(time_steps(lambda: plan.run_embeds_bf16(sb, ob), 10, flush, torch.cuda.current_stream()))
+        bytes16 = 2 * N * 256 * 2 + N * N * 4 + 2 * 100 * 8
+        gbs16 = Bm * bytes16 / (ms16 * 1e-3) / 1e9
+        row["bf16"] = {"ms": ms16, "algorithmic_bytes_per_image": bytes16, "achieved_gbs": gbs16,
+                       "frac_of_hbm_peak": gbs16 / pk["hbm_gbs"], "images_per_sec": Bm / (ms16 * 1e-3)}
+        out.append(row)
     return out
 
 

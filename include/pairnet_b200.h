@@ -252,6 +252,16 @@ PN_API int pn_ppn_forward(const float* query, const float* query_obj, const PnMl
                    int64_t* topk_idx /* [B,K] nullable */, int64_t* sub_pos /* [B,K] */,
                    int64_t* obj_pos /* [B,K] */, float* pair_feat /* [B,2K,256] nullable */,
                    int B, int N, int K, void* ws, size_t ws_bytes, pn_stream_t stream);
+/* bf16 variant of the "pair matrix + top-k only" mode ("bf16 variants take __nv_bfloat16* for activations,
+ * fp32 for importance and logits"; BASELINE config 5, "fp32 (and a bf16 run)"; pairnet_head.py:327-340 with the embeddings
+ * stored as bf16).  sub_embed / obj_embed: [B,N,256] bf16 bit patterns (`__nv_bfloat16`, passed as uint16_t so that this
+ * header stays plain C).  One tcgen05.mma kind::f16 pass (bf16 x bf16 products are exact in the fp32 accumulator), the
+ * matrix is written once as fp32 and the top-k runs on the tensor-memory accumulator.  N % 4 == 0, K <= 256. */
+PN_API size_t pn_ppn_pair_topk_bf16_workspace_bytes(int B);
+PN_API int pn_ppn_pair_topk_bf16(const uint16_t* sub_embed, const uint16_t* obj_embed,
+                   float* importance /* [B,N,N] */, int64_t* topk_idx /* [B,K] nullable */,
+                   int64_t* sub_pos /* [B,K] */, int64_t* obj_pos /* [B,K] */,
+                   int B, int N, int K, void* ws, size_t ws_bytes, pn_stream_t stream);
 /* stand-alone pieces (stage-wise parity tests) */
 PN_API int pn_conv_tiny(const float* x /* [B,N,N] */, const PnConvTiny* conv, float* y /* [B,N,N] */,
                  int B, int N, void* ws, size_t ws_bytes, pn_stream_t stream);

@@ -133,6 +133,8 @@ SIGNATURES = {
     "pn_ppn_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "pn_ppn_forward": (i32, [vp, vp, P(PnMlp3), P(PnMlp3), P(PnConvTiny), vp, vp, vp, vp, vp, vp, i32, i32, i32,
                              vp, sz, vp]),
+    "pn_ppn_pair_topk_bf16_workspace_bytes": (sz, [i32]),
+    "pn_ppn_pair_topk_bf16": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
     "pn_conv_tiny": (i32, [vp, P(PnConvTiny), vp, i32, i32, vp, sz, vp]),
     "pn_topk_pairs": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "pn_rel_prepared_bytes": (sz, [P(PnRelWeights)]),

@@ -622,7 +622,7 @@ static int ppn_forward(const float* query, const float* query_obj, const PnMlp3*
       pair_topk_fused_supported(N, D, K)) {
     // micro-benchmark 5a at scale: ONE pass over HBM -- the top-k runs on the tensor-memory accumulator inside the
     // pair-matrix kernel; images it flags (candidate overflow: constant / adversarial matrices) go to the exact kernel
-    PN_TRY(launch_pair_topk_fused(S, O, importance, topk_idx, sub_pos, obj_pos, redo, B, N, D, K, st));
+    PN_TRY(launch_pair_topk_fused(S, O, false, importance, topk_idx, sub_pos, obj_pos, redo, B, N, D, K, st));
     return launch_topk_pairs(importance, topk_idx, sub_pos, obj_pos, query, nullptr, B, N, K, st, redo);
   }
   if (!conv && raw == importance && (size_t)B * img_bytes > PPN_L2_CHUNK_BYTES) {
@@ -1046,6 +1046,25 @@ int pn_ppn_forward(const float* query, const float* query_obj, const PnMlp3* sub
   Workspace W(ws, ws_bytes);
   return ppn_forward(query, query_obj, sub_mlp, obj_mlp, conv, importance_raw, importance, topk_idx, sub_pos, obj_pos,
                      pair_feat, B, N, K, W, as_stream(stream));
+}
+
+size_t pn_ppn_pair_topk_bf16_workspace_bytes(int B) { return sizeof(int) * (size_t)(B > 0 ? B : 0) + 1024; }
+
+int pn_ppn_pair_topk_bf16(const uint16_t* sub_embed, const uint16_t* obj_embed, float* importance, int64_t* topk_idx,
+                          int64_t* sub_pos, int64_t* obj_pos, int B, int N, int K, void* ws, size_t ws_bytes,
+                          pn_stream_t stream) {
+  g_launches = 0;
+  PN_REQUIRE(sub_embed && obj_embed && importance && sub_pos && obj_pos && B > 0, PN_ERR_BAD_ARG, "ppn bf16: bad args");
+  PN_REQUIRE(ws, PN_ERR_WORKSPACE, "ppn bf16: null workspace");
+  PN_REQUIRE(get_option(OPT_TENSOR_CORES), PN_ERR_UNSUPPORTED, "ppn bf16: the bf16 path exists on tcgen05 only");
+  PN_REQUIRE(pair_topk_fused_supported(N, D, K, true), PN_ERR_UNSUPPORTED, "ppn bf16: N=%d K=%d unsupported", N, K);
+  Workspace W(ws, ws_bytes);
+  int* redo = W.take<int>((size_t)B);
+  PN_REQUIRE(W.ok() && !W.dry, PN_ERR_WORKSPACE, "ppn bf16: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  PN_TRY(launch_pair_topk_fused(sub_embed, obj_embed, true, importance, topk_idx, sub_pos, obj_pos, redo, B, N, D, K, st));
+  // images the fused kernel flagged (candidate overflow: constant / adversarial matrices) go to the exact kernel
+  return launch_topk_pairs(importance, topk_idx, sub_pos, obj_pos, nullptr, nullptr, B, N, K, st, redo);
 }
 
 int pn_conv_tiny(const float* x, const PnConvTiny* conv, float* y, int B, int N, void* ws, size_t ws_bytes,

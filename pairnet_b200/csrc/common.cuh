@@ -235,8 +235,9 @@ int launch_topk_pairs(const float* imp, int64_t* topk_idx, int64_t* sub_pos, int
 size_t conv_tiny_tc_workspace_bytes(int B, int N);
 int launch_conv_tiny_tc(const float* x, const PnConvTiny* cv, float* y, int B, int N, void* ws, size_t ws_bytes,
                         cudaStream_t st);
-bool pair_topk_fused_supported(int N, int K, int topk);
-int launch_pair_topk_fused(const float* S, const float* O, float* C, int64_t* topk_idx, int64_t* sub_pos,
+bool pair_topk_fused_supported(int N, int K, int topk, bool bf16 = false);
+// S, O: fp32 [B,N,K] (bf16 = false, 3xTF32) or __nv_bfloat16 [B,N,K] (bf16 = true, one kind::f16 pass)
+int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, int64_t* topk_idx, int64_t* sub_pos,
                            int64_t* obj_pos, int* redo, int B, int N, int K, int topk, cudaStream_t st);
 
 }  // namespace pn

@@ -180,14 +180,19 @@ struct Ring {  // (slot, phase) walker over a ring of runtime depth
   }
 };
 
+// BF16 = true: S and O are bf16 (`__nv_bfloat16` [B, N, 256]); one tcgen05.mma kind::f16 pass per 16 channels replaces the
+// three TF32 passes, a k-block is 64 channels (the same 128-byte swizzle row), and there is nothing to split: the MMA
+// warp takes the raw ring directly and the splitter warps are not launched.  The matrix and the top-k stay fp32 / int64.
+template <bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_constant__ Params prm) {
+  constexpr int BKE = BF16 ? 64 : BK;  // channels per k-block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int stage_bytes = prm.s_tile + prm.o_tile;
   const int RS = prm.raw_stages;
   uint8_t* raw_ring = smem;
   uint8_t* lo_ring = smem + (size_t)RS * stage_bytes;
-  uint8_t* out_stage = lo_ring + (size_t)LO_SLOTS * stage_bytes + TAIL_PAD;  // [8 warps][32 rows x 128 B], swizzled
+  uint8_t* out_stage = lo_ring + (size_t)(BF16 ? 0 : LO_SLOTS) * stage_bytes + TAIL_PAD;  // [8 warps][32 rows x 128 B], swizzled
   uint8_t* ctrl = out_stage + NUM_EPI_WARPS * STAGE_TILE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [RS<=8] TMA -> splitters
   uint64_t* empty_bar = full_bar + 8;                       // [RS<=8] MMA -> TMA
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_base_slot);
-  const int num_kb = prm.K / BK;
+  const int num_kb = prm.K / BKE;
   const int tiles_per_img = prm.mtiles * prm.ntiles;
   const int N = prm.N;
 
@@ -241,11 +246,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
           if (elect_one()) {
             mbar_expect_tx(&full_bar[r.slot], stage_tx);
             if (reuse) {
-              tma_load_3d_hint(st, &prm.s_map, &full_bar[r.slot], kb * BK, m0, b, pol_keep);
-              tma_load_3d_hint(st + prm.s_tile, &prm.o_map, &full_bar[r.slot], kb * BK, n0, b, pol_keep);
+              tma_load_3d_hint(st, &prm.s_map, &full_bar[r.slot], kb * BKE, m0, b, pol_keep);
+              tma_load_3d_hint(st + prm.s_tile, &prm.o_map, &full_bar[r.slot], kb * BKE, n0, b, pol_keep);
             } else {
-              tma_load_3d(st, &prm.s_map, &full_bar[r.slot], kb * BK, m0, b);
-              tma_load_3d(st + prm.s_tile, &prm.o_map, &full_bar[r.slot], kb * BK, n0, b);
+              tma_load_3d(st, &prm.s_map, &full_bar[r.slot], kb * BKE, m0, b);
+              tma_load_3d(st + prm.s_tile, &prm.o_map, &full_bar[r.slot], kb * BKE, n0, b);
             }
           }
           __syncwarp();
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform loop, one elected lane issues)
-    const uint32_t idesc = make_idesc(prm.bn);
+    const uint32_t idesc = BF16 ? make_idesc_bf16(prm.bn) : make_idesc(prm.bn);
     Ring r(RS), l(LO_SLOTS);
     uint32_t tile_it = 0;
     for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
@@ -264,6 +269,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)prm.acc_stride;
         for (int kb = 0; kb < num_kb; ++kb, r.next(), l.next()) {
+          if (BF16) {
+            mbar_wait(&full_bar[r.slot], r.phase);  // bf16 tiles are MMA operands as they land
+            tc_fence_after();
+            const uint32_t op = smem_u32(raw_ring + (size_t)r.slot * stage_bytes);
+            const uint64_t a = make_smem_desc(op), bd = make_smem_desc(op + prm.s_tile);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BKE / UMMA_K_BF16; ++k) {
+                const uint64_t koff = (uint64_t)((k * UMMA_K_BF16 * 2) >> 4);
+                umma_bf16(d_tmem, a + koff, bd + koff, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+              }
+              umma_commit(&empty_bar[r.slot]);
+            }
+            __syncwarp();
+            continue;
+          }
           mbar_wait(&split_bar[l.slot], l.phase);  // lo tiles written (and, transitively, the raw tiles landed)
           tc_fence_after();
           const uint32_t hi = smem_u32(raw_ring + (size_t)r.slot * stage_bytes);
@@ -450,7 +471,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tiles outlive their stores
     tc_fence_before();
-  } else {
+  } else if (!BF16) {
     // ===== splitters: lo tiles of S and O (16-byte chunks, swizzled layout preserved); the raw tile is the hi operand
     const int sid = threadIdx.x - (64 + 32 * NUM_EPI_WARPS);  // 0 .. 255
     constexpr int NSPLIT = 32 * NUM_SPLIT_WARPS;
@@ -496,7 +517,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map_3d(CUtensorMap* map, const float* ptr, int B, int N, int K, int box_rows, int box_cols = BK) {
+static int make_map_3d(CUtensorMap* map, const void* ptr, int B, int N, int K, int box_rows, int box_cols = BK,
+                       bool bf16 = false) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -508,10 +530,12 @@ static int make_map_3d(CUtensorMap* map, const float* ptr, int B, int N, int K, 
   PN_REQUIRE(fn, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   PN_REQUIRE(((uintptr_t)ptr & 15) == 0, PN_ERR_UNSUPPORTED, "pair top-k: embeddings must be 16B aligned");
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)N * K * 4};
+  const cuuint64_t es = bf16 ? 2 : 4;
+  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)N * K * es};
   cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
@@ -521,20 +545,21 @@ static int make_map_3d(CUtensorMap* map, const float* ptr, int B, int N, int K, 
 }  // namespace pairtopk
 
 // the fused kernel thresholds on 2 local maxima (even / odd 32-column chunks) per row of the image's first tile
-bool pair_topk_fused_supported(int N, int K, int topk) {
+bool pair_topk_fused_supported(int N, int K, int topk, bool bf16) {
   const int rows0 = N < pairtopk::BM ? N : pairtopk::BM;
+  const int bke = bf16 ? 64 : pairtopk::BK;
   return topk >= 1 && topk <= pairtopk::TOPK_MAX && topk <= (N > 32 ? 2 : 1) * rows0 && N >= 2 && (N & 3) == 0 &&
-         K % pairtopk::BK == 0 && K >= pairtopk::BK && (long long)N * N < (1ll << 31);
+         K % bke == 0 && K >= bke && (long long)N * N < (1ll << 31);
 }
 
 // importance[b] = S[b] . O[b]^T (3xTF32 on tcgen05) with the top-k pair select fused into the epilogue.
 // redo [B] int: set to 1 for images the caller must pass to `launch_topk_pairs` (exact kernel), 0 otherwise.
-int launch_pair_topk_fused(const float* S, const float* O, float* C, int64_t* topk_idx, int64_t* sub_pos,
+int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, int64_t* topk_idx, int64_t* sub_pos,
                            int64_t* obj_pos, int* redo, int B, int N, int K, int topk, cudaStream_t st) {
   using namespace pairtopk;
   PN_REQUIRE(S && O && C && sub_pos && obj_pos && redo && B > 0, PN_ERR_BAD_ARG, "pair top-k: bad args");
-  PN_REQUIRE(pair_topk_fused_supported(N, K, topk), PN_ERR_UNSUPPORTED, "pair top-k: N=%d K=%d topk=%d unsupported", N,
-             K, topk);
+  PN_REQUIRE(pair_topk_fused_supported(N, K, topk, bf16), PN_ERR_UNSUPPORTED,
+             "pair top-k: N=%d K=%d topk=%d unsupported", N, K, topk);
   Params prm{};
   prm.C = C; prm.topk_idx = topk_idx; prm.sub_pos = sub_pos; prm.obj_pos = obj_pos; prm.redo = redo;
   prm.B = B; prm.N = N; prm.K = K; prm.topk = topk;
@@ -547,28 +572,32 @@ int launch_pair_topk_fused(const float* S, const float* O, float* C, int64_t* to
   const int o_box = prm.n_step;
   prm.s_tile = s_box * BK * 4;
   prm.o_tile = o_box * BK * 4;
-  PN_TRY(make_map_3d(&prm.s_map, S, B, N, K, s_box));
-  PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box));
+  PN_TRY(make_map_3d(&prm.s_map, S, B, N, K, s_box, bf16 ? 64 : BK, bf16));
+  PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box, bf16 ? 64 : BK, bf16));
   PN_TRY(make_map_3d(&prm.c_map, C, B, N, N, 32, 32));
   const int stage = prm.s_tile + prm.o_tile;
   const int fixed = 1024 + TAIL_PAD + NUM_EPI_WARPS * STAGE_TILE + CTRL_BYTES + (int)sizeof(TopkSmem) + 64;
-  int rs = (SMEM_LIMIT - fixed) / stage - LO_SLOTS;
+  const int lo_slots = bf16 ? 0 : LO_SLOTS;
+  int rs = (SMEM_LIMIT - fixed) / stage - lo_slots;
   rs = rs > 8 ? 8 : rs;
   PN_REQUIRE(rs >= 2, PN_ERR_UNSUPPORTED, "pair top-k: tiles of N=%d do not fit shared memory", N);
   prm.raw_stages = rs;
   prm.acc_stride = prm.bn <= 128 ? 128 : 256;
   prm.tmem_cols = 2 * prm.acc_stride;
-  const size_t smem = (size_t)fixed + (size_t)(rs + LO_SLOTS) * stage;
+  const size_t smem = (size_t)fixed + (size_t)(rs + lo_slots) * stage;
   static bool attr_done[PN_MAX_DEVICES] = {false};  // the attribute is per device
   bool& attr_set = attr_done[current_device()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pair_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(pair_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(pair_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     PN_REQUIRE(e == cudaSuccess, (int)e, "pair top-k: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int num_sms = sm_count();
   const int grid = B < num_sms ? B : num_sms;
-  pair_topk_kernel<<<grid, NUM_THREADS, smem, st>>>(prm);
+  if (bf16) pair_topk_kernel<true><<<grid, NUM_THREADS - 32 * NUM_SPLIT_WARPS, smem, st>>>(prm);  // no splitter warps
+  else pair_topk_kernel<false><<<grid, NUM_THREADS, smem, st>>>(prm);
   return check_launch("pair_topk_kernel");
 }
 

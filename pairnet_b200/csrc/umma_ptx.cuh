@@ -108,6 +108,30 @@ __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return d;
 }
 
+// kind::f16 with bf16 operands (16 elements = 32 bytes of K per instruction: the same byte geometry as kind::tf32, so the
+// shared-memory descriptors and the k-advance inside a swizzle row are unchanged), fp32 accumulate
+constexpr int UMMA_K_BF16 = 16;
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // D format: F32
+  d |= 1u << 7;                    // A format: BF16
+  d |= 1u << 10;                   // B format: BF16
+  d |= (uint32_t)(bn >> 3) << 17;  // N
+  d |= (uint32_t)(128 >> 4) << 24; // M = 128
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // round to nearest TF32, ties away from zero -- what cvt.rna.tf32.f32 computes -- as two integer ops: add half a TF32 ulp
 // to the magnitude bits, clear the low 13.  ptxas expands the cvt into ~9 instructions (NaN / Inf selects); this
 // form is bit-identical for every finite input and Inf, and keeps quiet NaNs NaN.

@@ -213,6 +213,19 @@ class PpnPlan:
                                             _stream(sub_embed)), "pn_ppn_forward")
         return self.importance, self.idx, self.sub_pos, self.obj_pos
 
+    def run_embeds_bf16(self, sub_embed, obj_embed):
+        """bf16 microbench mode (``pn_ppn_pair_topk_bf16``): bf16 embeddings -> fp32 pair matrix + int64 top-k."""
+        if sub_embed.dtype != torch.bfloat16 or obj_embed.dtype != torch.bfloat16:
+            raise TypeError("run_embeds_bf16 takes torch.bfloat16 embeddings")
+        if not (sub_embed.is_contiguous() and obj_embed.is_contiguous()):
+            raise ValueError("embeddings must be contiguous [B,N,256]")
+        nat.check(nat.load().pn_ppn_pair_topk_bf16(sub_embed.data_ptr(), obj_embed.data_ptr(),
+                                                   self.importance.data_ptr(), self.idx.data_ptr(),
+                                                   self.sub_pos.data_ptr(), self.obj_pos.data_ptr(), self.B, self.N,
+                                                   self.K, self.ws.data_ptr(), self.need, _stream(sub_embed)),
+                  "pn_ppn_pair_topk_bf16")
+        return self.importance, self.idx, self.sub_pos, self.obj_pos
+
 
 def gather_rows(src, idx):
     """src [B,Nsrc,...], idx [B,R] int64 -> [B,R,...]."""

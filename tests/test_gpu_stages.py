@@ -606,6 +606,49 @@ def test_pair_topk_fused_adversarial_images_take_the_exact_path(N):
         assert torch.equal(sp[b].cpu() * N + op[b].cpu(), want), b
 
 
+@pytest.mark.parametrize("B,N", [(12, 100), (7, 200), (3, 400), (30, 52), (9, 128), (8, 132), (600, 100), (5, 256),
+                                 (4, 388), (1, 100), (2, 100), (150, 104), (3, 512)])
+def test_pair_topk_bf16(B, N):
+    """bf16 entry point (`pn_ppn_pair_topk_bf16`, SURVEY 8b / config 5 "bf16 run"): bf16 x bf16 products are exact in
+    fp32, so the matrix equals the fp64 product of the bf16-rounded embeddings to fp32 summation noise; indices are
+    bit-exact for the matrix the kernel wrote (ties by ascending flat index)."""
+    import torch.nn.functional as F
+    from oracle.head import stable_topk
+    from pairnet_b200 import ops
+    K = 100
+    g = torch.Generator().manual_seed(2000 + N)
+    s = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1).to(torch.bfloat16)
+    o = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1).to(torch.bfloat16)
+    if B >= 8:  # adversarial images: constant matrix, N-fold ties, duplicated columns -> flagged, exact kernel
+        s[1] = s[1, :1]
+        o[1] = o[1, :1]
+        s[4, :, :] = s[4, :1]
+        o[6, N // 2:] = o[6, :N - N // 2]
+    plan = ops.PpnPlan(B, N, K, "cuda")
+    imp, idx, sp, op = plan.run_embeds_bf16(s.cuda(), o.cuda())
+    torch.cuda.synchronize()
+    ref = torch.matmul(s.double(), o.double().transpose(1, 2))
+    assert float((imp.cpu().double() - ref).abs().max()) < 1e-6
+    for b in range(B):
+        want = torch.from_numpy(stable_topk(imp[b].flatten().cpu().numpy(), K))
+        assert torch.equal(idx[b].cpu(), want), b
+        assert torch.equal(sp[b].cpu() * N + op[b].cpu(), want), b
+    # the fp32 entry point on the same (bf16-representable) values writes the same matrix to fp32 noise
+    imp32 = ops.PpnPlan(B, N, K, "cuda").run_embeds(s.float().cuda(), o.float().cuda())[0]
+    assert float((imp32 - imp).abs().max()) < 2e-6
+
+
+def test_pair_topk_bf16_rejects_fp32_and_bad_shapes():
+    from pairnet_b200 import _native as nat, ops
+    plan = ops.PpnPlan(4, 100, 100, "cuda")
+    with pytest.raises(TypeError):
+        plan.run_embeds_bf16(torch.zeros(4, 100, 256, device="cuda"), torch.zeros(4, 100, 256, device="cuda"))
+    bad = ops.PpnPlan(4, 101, 100, "cuda")   # N % 4 != 0: no silent fallback
+    z = torch.zeros(4, 101, 256, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(nat.NativeError):
+        bad.run_embeds_bf16(z, z)
+
+
 def test_ppn_l2_chunked_batch_equals_unchunked():
     """Batches whose pair matrices exceed the L2 chunk budget are walked chunk by chunk: same results."""
     import torch.nn.functional as F
