@@ -578,6 +578,51 @@ def config4_head_bench(device, flush, stream):
             "dtype": "fp32 (3xTF32); bf16 path and Swin-L backbone not built -> extrapolated config, head only"}
 
 
+def config4_e2e_bench(device, flush, stream):
+    """BASELINE config 4 end to end on one GPU's share (bs 8 over 8 GPUs = 1 image per GPU): Swin-L backbone
+    (`configs/mask2former/pairnet_swinb.py` with SURVEY 8d's Swin-L numbers: embed 192, heads 6/12/24/48, in_channels
+    192..1536), 200 object / 200 relation queries, 1024x1024 synthetic input.  bf16-class arithmetic: the backbone runs
+    under bf16 autocast (PyTorch plumbing), the hand-written pixel-decoder / head kernels in PN_OPT_SINGLE_PASS mode (one
+    TF32 tensor pass, fp32 storage).  Random-init weights, eager launches, pinned-host H2D + D2H of the class scores
+    inside the timed region."""
+    from pairnet_b200 import _native as nat
+    from pairnet_b200.registry import Config, build_detector
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_swinl_200q_b200.py"))
+    torch.manual_seed(10086)
+    model = build_detector(cfg.model)
+    model.init_weights()
+    model = model.to(device).eval()
+    model.backbone_autocast = torch.bfloat16
+    img_host = torch.randn(1, 3, 1024, 1024, generator=torch.Generator().manual_seed(44)).pin_memory()
+    lib = nat.load()
+    lib.pn_set_option(nat.PN_OPT_SINGLE_PASS, 1)
+    try:
+        def step():
+            out = model.forward_dummy(img_host.to(device, non_blocking=True))
+            return out[0]["rel"].to("cpu", non_blocking=True)
+        with torch.no_grad():
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            ms = statistics.mean(time_steps(step, 10, flush, stream))
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            x = img_host.to(device)
+            metas = [dict(batch_input_shape=(1024, 1024), img_shape=(1024, 1024, 3))]
+            e0.record(); feats = model.extract_feat(x); e1.record(); model.bbox_head(feats, metas); e2.record()
+            torch.cuda.synchronize()
+    finally:
+        lib.pn_set_option(nat.PN_OPT_SINGLE_PASS, 0)
+    n_params = sum(p.numel() for p in model.backbone.parameters())
+    del model
+    torch.cuda.empty_cache()
+    return {"what": "BASELINE config 4, one GPU's share: Swin-L (bf16 autocast, PyTorch plumbing) + pixel decoder + "
+                    "CrossHead2 at 200/200 queries, 1024x1024, 1 image per GPU, eager launches, H2D + D2H inside the timed region",
+            "ms_per_image": ms, "images_per_sec_per_gpu": 1e3 / ms, "backbone_ms": e0.elapsed_time(e1),
+            "pixel_decoder_plus_head_ms": e1.elapsed_time(e2), "backbone_params": n_params,
+            "dtype": "bf16-class: backbone bf16 autocast; pixel decoder + head single-pass TF32 on fp32 storage",
+            "note": "extrapolated config (the reference ships Swin-B / 100 queries); Swin restated from mmdet 2.25.1, parity unpinned"}
+
+
 def train_bench(device, rank, world, steps):
     """BASELINE config 3 shape at fp32: one data-parallel TRAINING step per rank on bs = 2 synthetic 800x1333 images with
     synthetic targets (12 masks, 10 triplets per image): forward (backbone / pixel decoder on the no-grad CUDA path, head
@@ -743,6 +788,7 @@ def run_b200(args, rank, world, local):
                   if (rank == 0 and world == 1 and not args.no_ppn_microbench) else None)
         e2e_st = e2e_simple_test(model, imgs_host, device, flush, stream, min(args.steps, 10)) if rank == 0 else None
         cfg4 = config4_head_bench(device, flush, stream) if (rank == 0 and not args.no_ppn_microbench) else None
+        cfg4e = config4_e2e_bench(device, flush, stream) if (rank == 0 and not args.no_ppn_microbench) else None
 
     train = None
     if not args.no_train:
@@ -792,6 +838,7 @@ def run_b200(args, rank, world, local):
         line["train_step"] = train
     if cfg4 is not None:
         line["config4_head"] = cfg4
+        line["config4_e2e"] = cfg4e
     if reduced is not None:
         line["reduced_precision_arm"] = reduced
     if post is not None:

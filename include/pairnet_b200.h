@@ -106,6 +106,12 @@ PN_API int pn_get_option(int key);
                                     memory-side tcgen05 GEMMs (K/V projections, mask einsums, pixel-decoder encoder) and the masked
                                     cross-attention run ONE kind::tf32 pass on the raw fp32 operands (10-bit mantissa >= bf16's 8);
                                     the pair matrix, ConvTiny and the top-k stay at fp32 parity */
+#define PN_OPT_NVTX 15           /* default 1: NVTX v3 ranges around the stages of the hot path (pn::m2f_decoder, pn::m2f_layer,
+                                    pn::ppn, pn::relation_fusion, pn::output_gathers); no-ops unless a profiler is attached */
+#define PN_OPT_PDL 16            /* default 1: the small kernels of the query-side chain (skinny GEMM, LayerNorm, small attention, row
+                                    ops) are launched with programmatic stream serialization (under graph capture: programmatic
+                                    edges); each waits with griddepcontrol.wait before touching activations, the skinny GEMM
+                                    fetches its (static) weights ahead of the wait.  0 = plain serialized launches */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

@@ -42,6 +42,8 @@ struct MhaKernelArgs {
 };
 
 __global__ void __launch_bounds__(ATT_THREADS) mha_kernel(const MhaKernelArgs a) {
+  pdl_wait();     // PDL contract (common.cuh): nothing is read or written before the preceding grid has completed
+  pdl_trigger();
   __shared__ __align__(16) float ks[2][ATT_TK][HD];
   __shared__ __align__(16) float vs[2][ATT_TK][HD];
   const int split = blockIdx.x, h = blockIdx.y;
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(ATT_THREADS) mha_kernel(const MhaKernelArgs a)
 __global__ void __launch_bounds__(256) mha_combine_kernel(const float* __restrict__ opart,
                                                            const float2* __restrict__ ml, float* __restrict__ out,
                                                            int B, int Nq, int S) {
+  pdl_wait();     // PDL contract (common.cuh)
+  pdl_trigger();
   const int bq = blockIdx.x;
   const int b = bq / Nq, qi = bq % Nq;
   const int c = threadIdx.x, h = c / HD;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(256) mha_combine_kernel(const float* __restric
 // split granularity: whole 64-key tiles when the mask is present (bit words are addressed per tile); 16 keys
 // otherwise, so the 100-key self-attention and 200-key relation attention still spread over >100 CTAs.
 int launch_mha_combine(const float* opart, const float2* ml, float* out, int B, int Nq, int S, cudaStream_t st) {
-  mha_combine_kernel<<<B * Nq, 256, 0, st>>>(opart, ml, out, B, Nq, S);
+  launch_pdl(mha_combine_kernel, dim3(B * Nq), dim3(256), 0, st, opart, ml, out, B, Nq, S);
   return check_launch("mha_combine_kernel");
 }
 
@@ -256,10 +260,10 @@ int launch_mha(const MhaArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
     k.ml = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) + o);
   }
   dim3 grid(k.splits, NH, a.B * cdiv(a.Nq, ATT_THREADS));
-  mha_kernel<<<grid, ATT_THREADS, 0, st>>>(k);
+  launch_pdl(mha_kernel, grid, dim3(ATT_THREADS), 0, st, k);
   PN_TRY(check_launch("mha_kernel"));
   if (k.splits > 1) {
-    mha_combine_kernel<<<a.B * a.Nq, 256, 0, st>>>(k.opart, k.ml, a.out, a.B, a.Nq, k.splits);
+    launch_pdl(mha_combine_kernel, dim3(a.B * a.Nq), dim3(256), 0, st, k.opart, k.ml, a.out, a.B, a.Nq, k.splits);
     PN_TRY(check_launch("mha_combine_kernel"));
   }
   return 0;

@@ -43,6 +43,22 @@ int sm_count();  // SMs of the current device (api.cu)
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// The query-side chain of the head is ~230 dependent launches of 3-10 us kernels: launch latency, not work, bounds it.
+// Kernels of that chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization (under stream capture: a
+// programmatic graph edge), so kernel N+1 is scheduled and runs its prologue while kernel N is still executing.
+// Contract: every kernel launched through `launch_pdl` executes `pdl_wait()` before it touches anything another kernel
+// may have written or may still read (it blocks until the preceding grid has completed and flushed), and only THEN
+// `pdl_trigger()` -- so when a dependent starts early, everything older than its immediate predecessor is complete.
+// Code before `pdl_wait()` may only read data that no kernel of the forward writes (model weights, prepared blobs).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args);
+#endif
+
 // ---- bump allocator over the caller's workspace ------------------------------------------------
 struct Workspace {
   char* base;
@@ -79,6 +95,7 @@ struct GemmProb {
   long long sA, sW, sC, sR;     // batch strides (elements)
   int splits;                   // split-K (>=1); partial s goes to C + s*split_stride, no epilogue
   long long split_stride;
+  int w_static;                 // W is a model weight (no kernel of the forward writes it): may be fetched before pdl_wait()
 };
 constexpr int GEMM_MAX_PROBS = 12;
 struct GemmBatch {
@@ -213,7 +230,7 @@ int launch_level_prep(const float* mem, const float* level_embed, const float* p
 int launch_level_prep_tokens(const float* mem, long long bstride, const float* level_embed, const float* pos, float* x,
                              float* xp, int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_PPN_FUSED_TOPK = 11, OPT_CONV_TC = 12, OPT_UMMA_TMA_STORE = 13, OPT_SINGLE_PASS = 14, OPT_COUNT = 15 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_PPN_FUSED_TOPK = 11, OPT_CONV_TC = 12, OPT_UMMA_TMA_STORE = 13, OPT_SINGLE_PASS = 14, OPT_NVTX = 15, OPT_PDL = 16, OPT_COUNT = 17 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);
@@ -239,5 +256,20 @@ bool pair_topk_fused_supported(int N, int K, int topk, bool bf16 = false);
 // S, O: fp32 [B,N,K] (bf16 = false, 3xTF32) or __nv_bfloat16 [B,N,K] (bf16 = true, one kind::f16 pass)
 int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, int64_t* topk_idx, int64_t* sub_pos,
                            int64_t* obj_pos, int* redo, int B, int N, int K, int topk, cudaStream_t st);
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = get_option(OPT_PDL) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 }  // namespace pn

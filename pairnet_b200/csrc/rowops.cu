@@ -64,6 +64,8 @@ __device__ __forceinline__ void store_split(const float (&v)[8], float* __restri
 
 // lane owns channels [4*lane, 4*lane+4) and [128+4*lane, 128+4*lane+4)
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  pdl_wait();     // PDL contract (common.cuh): nothing is read or written before the preceding grid has completed
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= a.M) return;
@@ -111,12 +113,17 @@ int launch_layernorm(const LnArgs& a, cudaStream_t st) {
   PN_REQUIRE((a.y_hi == nullptr) == (a.y_lo == nullptr) && (a.ypos_hi == nullptr) == (a.ypos_lo == nullptr),
              PN_ERR_BAD_ARG, "layernorm: split outputs come in hi/lo pairs");
   PN_REQUIRE(!a.y2 || (a.gamma2 && a.beta2), PN_ERR_BAD_ARG, "layernorm: y2 needs gamma2/beta2");
-  layernorm_kernel<<<cdiv(a.M, 8), 256, 0, st>>>(a);
+  // PDL only for the query-side chain (a few hundred rows, latency bound); the 43 900-token LayerNorms of the pixel-decoder
+  // encoder measured slightly slower with it (thousands of CTAs made resident early)
+  if (a.M <= 4096) launch_pdl(layernorm_kernel, dim3(cdiv(a.M, 8)), dim3(256), 0, st, a);
+  else layernorm_kernel<<<cdiv(a.M, 8), 256, 0, st>>>(a);
   return check_launch("layernorm_kernel");
 }
 
 // F.normalize(x, p=2, dim=-1, eps=1e-12): x / max(||x||_2, eps)      (pairnet_head.py:325-326)
 __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, int M) {
+  pdl_wait();     // PDL contract (common.cuh)
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x
   store_row(v, y + (size_t)m * D, lane);
 }
 int launch_l2norm(const float* x, float* y, int M, cudaStream_t st) {
-  l2norm_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, y, M);
+  launch_pdl(l2norm_kernel, dim3(cdiv(M, 8)), dim3(256), 0, st, x, y, M);
   return check_launch("l2norm_kernel");
 }
 
@@ -139,6 +146,8 @@ int launch_l2norm(const float* x, float* y, int M, cudaStream_t st) {
 __global__ void __launch_bounds__(256) bcast_rows_kernel(const float* __restrict__ a, const float* __restrict__ bpos,
                                                           float* __restrict__ out, float* __restrict__ out_sum,
                                                           int B, int N) {
+  pdl_wait();     // PDL contract (common.cuh)
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= B * N) return;
@@ -155,13 +164,15 @@ __global__ void __launch_bounds__(256) bcast_rows_kernel(const float* __restrict
   }
 }
 int launch_bcast_rows(const float* a, const float* b, float* out, float* out_sum, int B, int N, cudaStream_t st) {
-  bcast_rows_kernel<<<cdiv((long long)B * N, 8), 256, 0, st>>>(a, b, out, out_sum, B, N);
+  launch_pdl(bcast_rows_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), 0, st, a, b, out, out_sum, B, N);
   return check_launch("bcast_rows_kernel");
 }
 
 // out[b,n,:] = x[b,n,:] + pos[n,:]
 __global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ x, const float* __restrict__ pos,
                                                         float* __restrict__ out, int B, int N) {
+  pdl_wait();     // PDL contract (common.cuh)
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= B * N) return;
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__
   store_row(v, out + (size_t)m * D, lane);
 }
 int launch_add_rows(const float* x, const float* pos, float* out, int B, int N, cudaStream_t st) {
-  add_rows_kernel<<<cdiv((long long)B * N, 8), 256, 0, st>>>(x, pos, out, B, N);
+  launch_pdl(add_rows_kernel, dim3(cdiv((long long)B * N, 8)), dim3(256), 0, st, x, pos, out, B, N);
   return check_launch("add_rows_kernel");
 }
 
@@ -396,6 +407,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
                                                            const int64_t* __restrict__ idx,
                                                            float* __restrict__ dst, int Nsrc, int R, long long L,
                                                            int vec) {
+  pdl_wait();     // PDL contract (common.cuh)
+  pdl_trigger();
   const int br = blockIdx.x;
   const int b = br / R;
   long long row = idx[br];
@@ -418,7 +431,7 @@ int launch_gather_rows(const float* src, const int64_t* idx, float* dst, int B, 
   int chunks = cdiv(vec ? L / 4 : L, 256 * 8);
   chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
   dim3 grid(B * R, chunks);
-  gather_rows_kernel<<<grid, 256, 0, st>>>(src, idx, dst, Nsrc, R, L, vec);
+  launch_pdl(gather_rows_kernel, grid, dim3(256), 0, st, src, idx, dst, Nsrc, R, L, vec);
   return check_launch("gather_rows_kernel");
 }
 

@@ -83,8 +83,35 @@ __global__ void __launch_bounds__(32 * SK_WARPS) skinny_gemm_kernel(const __grid
 
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int nch = kw / 16;
+  // PDL: model weights of the first round are requested BEFORE waiting for the producer of A (the previous kernel of the
+  // chain) -- the weight round trip to L2 overlaps that kernel's tail; activations only after the wait
+  const bool w_early = P.w_static != 0;
   for (int c0 = 0; c0 < nch; c0 += SK_CHUNKS) {
     float4 ra[SK_CHUNKS][2 * MT], rw[SK_CHUNKS][NT];
+    if (c0 > 0 || w_early) {
+#pragma unroll
+      for (int c = 0; c < SK_CHUNKS; ++c) {
+        const bool live = c0 + c < nch;
+        const int ko = (c0 + c) * 16;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          rw[c][j] = (live && w_ok[j]) ? __ldg(reinterpret_cast<const float4*>(wp[j] + ko)) : zero4;
+      }
+    }
+    if (c0 == 0) {
+      pdl_wait();
+      pdl_trigger();
+      if (!w_early) {
+#pragma unroll
+        for (int c = 0; c < SK_CHUNKS; ++c) {
+          const bool live = c < nch;
+          const int ko = c * 16;
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            rw[c][j] = (live && w_ok[j]) ? __ldg(reinterpret_cast<const float4*>(wp[j] + ko)) : zero4;
+        }
+      }
+    }
 #pragma unroll
     for (int c = 0; c < SK_CHUNKS; ++c) {
       const bool live = c0 + c < nch;
@@ -92,9 +119,6 @@ __global__ void __launch_bounds__(32 * SK_WARPS) skinny_gemm_kernel(const __grid
 #pragma unroll
       for (int h = 0; h < 2 * MT; ++h)
         ra[c][h] = (live && a_ok[h]) ? __ldg(reinterpret_cast<const float4*>(ap[h] + ko)) : zero4;
-#pragma unroll
-      for (int j = 0; j < NT; ++j)
-        rw[c][j] = (live && w_ok[j]) ? __ldg(reinterpret_cast<const float4*>(wp[j] + ko)) : zero4;
     }
 #pragma unroll
     for (int c = 0; c < SK_CHUNKS; ++c) {
@@ -173,7 +197,7 @@ int launch_skinny_gemm(const GemmBatch& batch, int maxM, int maxN, int nz, cudaS
 #define PN_SKINNY(MT, NT)                                                    \
   do {                                                                       \
     dim3 grid(cdiv(maxN, 8 * NT), cdiv(maxM, 16 * MT), nz);                  \
-    skinny_gemm_kernel<MT, NT><<<grid, 32 * SK_WARPS, 0, st>>>(batch);       \
+    launch_pdl(skinny_gemm_kernel<MT, NT>, grid, dim3(32 * SK_WARPS), 0, st, batch); \
   } while (0)
   const long long tiles11 = (long long)cdiv(maxN, 8) * cdiv(maxM, 16) * nz;
   int v = variant;

@@ -120,6 +120,9 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const bool is_epi = warp >= 2 && warp < 2 + NUM_EPI_WARPS;
+  // (Not a PDL kernel: launching the persistent tcgen05 kernels with programmatic serialization, or letting them trigger
+  // their dependents early, made the pixel-decoder encoder 0.2 ms SLOWER on B200 -- measured, scratch/pdl_ab.py; the
+  // attribute is kept for the microsecond-scale kernels of the query-side chain only.)
   if (is_epi) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
     for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += 32 * NUM_EPI_WARPS) {
       const int pi = i / BIAS_MAX, n = i % BIAS_MAX;
@@ -476,6 +479,8 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
 // ---- hi/lo split (round-to-nearest tf32) ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                           float* __restrict__ lo, size_t n4, float scale) {
+  pdl_wait();     // PDL contract (common.cuh)
+  pdl_trigger();
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
@@ -567,7 +572,7 @@ int launch_split_tf32_scaled(const float* x, float* hi, float* lo, size_t n, flo
   const size_t n4 = n / 4;
   int blocks = (int)((n4 + 255) / 256);
   blocks = blocks > 148 * 16 ? 148 * 16 : (blocks < 1 ? 1 : blocks);
-  umma::split_tf32_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n4, scale);
+  launch_pdl(umma::split_tf32_kernel, dim3(blocks), dim3(256), 0, st, x, hi, lo, n4, scale);
   return check_launch("split_tf32_kernel");
 }
 

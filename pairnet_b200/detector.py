@@ -22,13 +22,20 @@ class PSGTr(nn.Module):
         self.bbox_head = build_head(bbox_head)
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.num_classes = self.bbox_head.num_classes
+        # reduced-precision upstream for the bf16-class configs (BASELINE configs 3-4): torch.bfloat16 runs the backbone
+        # under autocast; its feature maps are handed to the head as fp32 (the CUDA library's activation type)
+        self.backbone_autocast = None
 
     def init_weights(self):
         self.backbone.init_weights()
         self.bbox_head.init_weights()
 
     def extract_feat(self, img):
-        return self.backbone(img)
+        if self.backbone_autocast is None:
+            return self.backbone(img)
+        with torch.autocast(img.device.type, dtype=self.backbone_autocast):
+            feats = self.backbone(img)
+        return tuple(f.float() for f in feats)
 
     def forward_dummy(self, img):
         """psgtr.py:92-110."""

@@ -1,8 +1,14 @@
-"""UPSTREAM of the hot path ("next"): mmdet 2.25.1 ``MSDeformAttnPixelDecoder``
-(cfg ``configs/mask2former/pairnet.py:33-71``, call site ``pairnet_head.py:262``) as device-side
-PyTorch plumbing (cuDNN / cuBLAS / ``grid_sample``), batch-first.  It produces ``mask_features`` and
-the three memories the CUDA hot path consumes.  Parameter names follow mmdet so checkpoints load.
-Not hand-written CUDA yet -- listed as the next row to take over."""
+"""UPSTREAM of the hot path: mmdet 2.25.1 ``MSDeformAttnPixelDecoder``
+(cfg ``configs/mask2former/pairnet.py:33-71``, call site ``pairnet_head.py:262``), batch-first.  It produces
+``mask_features`` and the three memories the CUDA hot path consumes.  Parameter names follow mmdet so checkpoints load.
+
+On a CUDA device without autograd (inference, the frozen part of training) everything except the single 3x3 output
+convolution runs on the hand-written library: the six deformable-attention encoder layers (``pn_msda_encoder_forward``:
+tcgen05 GEMMs + ``msda_sample_kernel``), GroupNorm, the FPN top-down merge fused into the GN apply pass, the 1x1 input /
+lateral convolutions and the ``mask_feature`` 1x1 convolution as tcgen05 GEMMs on channels_last maps.  The 3x3
+``output_convs`` stay on cuDNN.  The PyTorch statements of the same modules below (``grid_sample`` encoder, ``nn.GroupNorm``,
+``nn.Conv2d``) are what runs under autograd or on the CPU -- upstream plumbing only, never the hot path -- and are the
+A/B reference of ``tests/test_gpu_stages.py``."""
 import ctypes as C
 import math
 
@@ -38,12 +44,54 @@ class ConvModule(nn.Module):
         self.gn = nn.GroupNorm(groups, cout)
         self.with_act = act
 
+    native_conv1x1 = True   # class-wide switch (A/B tests, bench): 1x1 convolutions on the tcgen05 GEMM
+
     def forward(self, x):
-        x = self.conv(x)
+        y = self._native_conv1x1(x) if (self.native_conv1x1 and not torch.is_grad_enabled()) else None
+        x = self.conv(x) if y is None else y
         if x.is_cuda and not torch.is_grad_enabled() and x.shape[1] == nat.EMBED_DIMS and x.dtype == torch.float32:
             return self._native_gn(x)
-        x = self.gn(x)
+        x = self.gn(x)   # autograd / CPU plumbing (never the hot path)
         return F.relu(x, inplace=True) if self.with_act else x
+
+    def _native_conv1x1(self, x):
+        """1x1 convolution of a dense channels_last map = [B*H*W, Cin] x [Cout, Cin]^T on `umma_gemm_kernel`.  Arithmetic
+        follows PyTorch's own convolution switch, as the cuDNN call it replaces did: ``torch.backends.cudnn.allow_tf32``
+        (default True, also in the reference's PyTorch 1.13) -> ONE kind::tf32 pass on the raw fp32 operands; False ->
+        3xTF32 (fp32 parity, 1e-5 class at K = 2048).  Returns None when the layout does not qualify (the caller then uses
+        cuDNN)."""
+        conv = self.conv
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and conv.kernel_size == (1, 1)
+                and conv.stride == (1, 1) and conv.groups == 1):
+            return None
+        B, Cin, H, W = x.shape
+        cout = conv.out_channels
+        if not (x.stride(1) == 1 and x.stride(3) == Cin and x.stride(2) == W * Cin and x.stride(0) == H * W * Cin
+                and x.data_ptr() % 16 == 0 and Cin % 32 == 0 and cout % 4 == 0 and cout <= 1024):
+            return None
+        lib = nat.load()
+        if lib.pn_get_option(nat.PN_OPT_TENSOR_CORES) == 0:
+            return None
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        bias = conv.bias.data_ptr() if conv.bias is not None else None
+        y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        if torch.backends.cudnn.allow_tf32:
+            wp = conv.weight.data_ptr()   # [Cout, Cin, 1, 1] contiguous = [Cout, Cin]; the tensor pipe truncates to TF32
+            nat.check(lib.pn_linear_tc_presplit(x.data_ptr(), x.data_ptr(), wp, wp, bias, y.data_ptr(), cout, B * H * W,
+                                                cout, Cin, 1, stream), "pn_linear_tc_presplit")
+            return y
+        key = (conv.weight.data_ptr(), conv.weight._version, str(x.device))
+        cache = self.__dict__.get("_w_split")
+        if cache is None or cache[0] != key:   # static weights: split once per weight version
+            blob = torch.empty(2 * cout * Cin, dtype=torch.float32, device=x.device)
+            nat.check(lib.pn_split_tf32(conv.weight.data_ptr(), blob.data_ptr(), blob.data_ptr() + cout * Cin * 4,
+                                        cout * Cin, stream), "pn_split_tf32")
+            cache = (key, blob)
+            self.__dict__["_w_split"] = cache
+        blob = cache[1]
+        nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), blob.data_ptr(), blob.data_ptr() + cout * Cin * 4, bias,
+                                        y.data_ptr(), cout, B * H * W, cout, Cin, stream), "pn_linear_tc_rawa")
+        return y
 
     def _native_gn(self, x):
         """pn_group_norm: two-pass HBM-bound GroupNorm(+ReLU), NCHW or channels_last storage, in place."""
@@ -324,7 +372,9 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 and t.data_ptr() % 16 == 0)
 
     def _native_lateral_merge(self, lat, feat, top):
-        cur = lat.conv(feat)
+        cur = lat._native_conv1x1(feat) if lat.native_conv1x1 else None
+        if cur is None:
+            cur = lat.conv(feat)
         if not (self._is_nhwc(cur) and cur.stride(0) == cur.shape[2] * cur.shape[3] * cur.shape[1]
                 and self._is_nhwc(top) and not lat.with_act):
             return None

@@ -292,6 +292,48 @@ def test_overlap_and_tensor_core_options_are_result_neutral(heads):
         lib.pn_set_option(0, 1)
 
 
+def test_programmatic_dependent_launch_is_result_neutral(heads):
+    """PN_OPT_PDL: the query-side chain launched with programmatic stream serialization (kernel N+1 starts while N is
+    still running and blocks in griddepcontrol.wait) gives bit-identical outputs to plain serialized launches -- eager,
+    repeated back to back (WAR hazards on the reused workspace would show up here), and under CUDA-graph replay."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    _, p = heads
+    mf, mems = _full_size_inputs(2, 56)
+    assert lib.pn_get_option(nat.PN_OPT_PDL) == 1
+    try:
+        lib.pn_set_option(nat.PN_OPT_PDL, 0)
+        base_cls, base_msk = _run_product(p, mf, mems)
+        base_cls = {k: v.clone() for k, v in base_cls.items()}
+        base_mask = base_msk["mask"].clone()
+        lib.pn_set_option(nat.PN_OPT_PDL, 1)
+        for _ in range(5):
+            c1, m1 = _run_product(p, mf, mems)
+            for k in base_cls:
+                assert torch.equal(base_cls[k], c1[k]), k
+            assert torch.equal(base_mask, m1["mask"])
+        # graph capture: the attribute becomes programmatic edges
+        mfc, memsc = mf.cuda(), [m.cuda() for m in mems]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(2):
+                p.forward_from_memories(mfc, memsc)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g):
+            gc, gm = p.forward_from_memories(mfc, memsc)
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        for k in base_cls:
+            assert torch.equal(base_cls[k], gc[k]), k
+        assert torch.equal(base_mask, gm["mask"])
+    finally:
+        lib.pn_set_option(nat.PN_OPT_PDL, 1)
+
+
 def test_channels_last_mask_features_and_mask_tc_option(heads):
     """mask_features handed over channels_last (token-major, what the native pixel decoder produces) gives the same
     bits as the NCHW input (which the library first copies to token-major); the FFMA mask kernels

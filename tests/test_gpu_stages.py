@@ -499,6 +499,44 @@ def test_pixel_decoder_native_tail_vs_torch():
     assert rel_err(mf_n, mf_t) < 1e-3  # the 3x3 output conv (cuDNN, TF32) is shared; the 1x1 is fp32-accurate here
 
 
+@pytest.mark.parametrize("cin,H,W,bias", [(2048, 25, 42, True), (1024, 50, 84, True), (512, 100, 167, True),
+                                          (256, 200, 334, False), (1536, 32, 32, True), (192, 64, 64, False)])
+def test_pixel_decoder_conv1x1_native_vs_cudnn_fp32(cin, H, W, bias):
+    """1x1 input / lateral convolutions of the pixel decoder on the tcgen05 GEMM (3xTF32) vs cuDNN with TF32 disabled
+    (true fp32), at the R50 (800x1333) and Swin-L (1024^2) channel counts; GroupNorm follows on the native kernel."""
+    from pairnet_b200.upstream.pixel_decoder import ConvModule
+    torch.manual_seed(cin)
+    m = ConvModule(cin, 256, 1, bias=bias).cuda().eval()
+    with torch.no_grad():
+        m.gn.weight.uniform_(0.5, 1.5)
+        m.gn.bias.normal_(0, 0.1)
+    x = _t((2, cin, H, W), 11 + cin).cuda().contiguous(memory_format=torch.channels_last)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            y_conv = m._native_conv1x1(x)
+            assert y_conv is not None and y_conv.is_contiguous(memory_format=torch.channels_last)
+            ref_conv = m.conv(x)
+            got = m(x)
+            ConvModule.native_conv1x1 = False
+            try:
+                ref = m(x)
+            finally:
+                ConvModule.native_conv1x1 = True
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    # 3xTF32: the tensor pipe accumulates with truncation, ~1e-5 of the scale at K = 2048 (DESIGN lesson 2)
+    assert rel_err(y_conv, ref_conv) < 3e-5
+    assert rel_err(got, ref) < 5e-5
+    # PyTorch's default (cudnn.allow_tf32 = True): one TF32 pass, like the cuDNN convolution it replaces
+    with torch.no_grad():
+        y_tf32, ref_tf32 = m._native_conv1x1(x), m.conv(x)
+    assert rel_err(y_tf32, ref_tf32) < 2e-3 and rel_err(y_tf32, ref_conv) < 2e-3
+    # a layout the GEMM does not take (NCHW-contiguous) is declined, not silently mis-read
+    assert m._native_conv1x1(x.contiguous()) is None or cin == 1
+
+
 @pytest.mark.parametrize("B,C,H,W", [(2, 64, 50, 67), (1, 64, 400, 667), (1, 8, 5, 4)])
 def test_maxpool3x3s2_nhwc_bit_exact(B, C, H, W):
     from pairnet_b200 import _native as nat
