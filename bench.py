@@ -633,9 +633,9 @@ def train_bench(device, rank, world, steps):
     metas = [dict(img_shape=(IMG_H, IMG_W, 3), batch_input_shape=(IMG_H, IMG_W)) for _ in range(PER_GPU_BATCH)]
     imgs = synthetic_images(PER_GPU_BATCH, 20000 + rank).to(device)
     rels, labels, masks = synthetic_targets(PER_GPU_BATCH, (IMG_H, IMG_W), 10086 + rank, device)
-    for scope in ("relation", "head"):
+    for scope in ("relation", "head", "head_bf16"):
         model = build_model(device)           # identical weights on every rank (seed 10086)
-        ts = TrainStep(model, scope=scope)
+        ts = TrainStep(model, scope=scope.split("_")[0], amp_dtype=torch.bfloat16 if scope.endswith("bf16") else None)
         torch.manual_seed(1234 + rank)        # sample points / dropout streams
         losses = None
         for _ in range(3):
@@ -657,9 +657,10 @@ def train_bench(device, rank, world, steps):
         ts.reducer.close()
         del ts, model
         torch.cuda.empty_cache()
-    out["what"] = ("fp32 training step, bs=2/GPU, frozen backbone + pixel decoder (no-grad CUDA path); scope 'relation' = "
+    out["what"] = ("training step, bs=2/GPU, frozen backbone + pixel decoder (no-grad CUDA path); scope 'relation' = "
                    "Pair-Net side trains on the CUDA library's decoder output, scope 'head' = everything after the pixel "
-                   "decoder trains; gradients all-reduced over NCCL in 25 MB buckets overlapped with backward")
+                   "decoder trains (fp32), 'head_bf16' = the same under bf16 autocast with fp32 master weights / gradients "
+                   "(BASELINE config 3's dtype); gradients all-reduced over NCCL in 25 MB buckets overlapped with backward")
     return out
 
 

@@ -50,7 +50,8 @@ class PSGTr(nn.Module):
         """psgtr.py:112-146.  ``gt_masks``: per image a ``[G,h,w]`` tensor (or an object with mmdet ``BitmapMasks``'
         ``to_ndarray()``); padded to the batch shape and resized to half resolution with nearest sampling."""
         import torch.nn.functional as F
-        with torch.no_grad():   # the backbone (and the pixel decoder inside the head) stay on the no-grad path
+        # the backbone (and the pixel decoder inside the head) stay on the no-grad path, outside any enclosing autocast
+        with torch.no_grad(), torch.autocast(img.device.type, enabled=False):
             x = self.extract_feat(img)
         if self.bbox_head.use_mask:
             assert gt_masks is not None

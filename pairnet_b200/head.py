@@ -185,11 +185,15 @@ class CrossHead2(TrainMixin, nn.Module):
         after the pixel decoder (PyTorch ops on the device, ``torch_head.py``)."""
         from . import torch_head as th
         scope = scope or self.train_scope
-        with torch.no_grad():
+        # the frozen, no-grad part runs on the CUDA library (fp32 tensors): an enclosing autocast (bf16 training) must not
+        # re-type its PyTorch plumbing
+        with torch.no_grad(), torch.autocast(feats[0].device.type, enabled=False):
             mask_features, memorys = self.pixel_decoder(feats)
         if scope == "relation":
             taps = {}
-            cls_scores, mask_preds = self.forward_from_memories(mask_features, memorys, taps=taps, materialize_seg=False)
+            with torch.autocast(feats[0].device.type, enabled=False):
+                cls_scores, mask_preds = self.forward_from_memories(mask_features, memorys, taps=taps,
+                                                                    materialize_seg=False)
             query_feat = taps["query_out"].transpose(0, 1).contiguous()      # [N,B,256], last decoder layer
             return th.relation_side(self, query_feat, cls_scores["cls"], mask_preds["mask"])[:2]
         if scope != "head":

@@ -38,8 +38,23 @@ class Result(object):
         yield self
 
 
+_PINNED_MIN_BYTES = 1 << 20
+
+
 def _np(t):
-    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else t
+    """Tensor -> numpy.  Large CUDA tensors (the [2K,H,W] boolean masks: 213 MB per 800x1333 image) are copied into a
+    PINNED host tensor from PyTorch's caching host allocator -- a pageable ``.cpu()`` runs at a fraction of the PCIe rate
+    (measured: 218 ms per bs = 2 step, almost all of it this copy).  The numpy array owns a reference to that tensor;
+    its block returns to the allocator's cache when the caller drops the result."""
+    if not isinstance(t, torch.Tensor):
+        return t
+    t = t.detach()
+    if t.is_cuda and t.numel() * t.element_size() >= _PINNED_MIN_BYTES:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host.numpy()
+    return t.cpu().numpy()
 
 
 def triplet2Result(triplets, use_mask, eval_mask_rels=False):

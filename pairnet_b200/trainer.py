@@ -93,8 +93,12 @@ def param_groups(named_params, lr, weight_decay):
 
 
 class TrainStep:
-    def __init__(self, model, scope="head", lr=1e-4, weight_decay=1e-4, max_norm=0.1, bucket_bytes=25 << 20):
+    def __init__(self, model, scope="head", lr=1e-4, weight_decay=1e-4, max_norm=0.1, bucket_bytes=25 << 20,
+                 amp_dtype=None):
+        """amp_dtype = torch.bfloat16: BASELINE config 3's bf16 training -- the differentiable head (torch ops) runs under
+        autocast, master weights, gradients (the all-reduced buckets) and AdamW state stay fp32."""
         self.model, self.scope, self.max_norm = model, scope, max_norm
+        self.amp_dtype = amp_dtype
         head = model.bbox_head
         head.train_scope = scope
         named = th.trainable_parameters(head, scope)
@@ -111,8 +115,10 @@ class TrainStep:
         self.num_params = sum(p.numel() for p in self.params)
 
     def __call__(self, img, img_metas, gt_rels, gt_labels, gt_masks):
-        losses = self.model.forward_train(img, img_metas, gt_rels=gt_rels, gt_bboxes=None, gt_labels=gt_labels,
-                                          gt_masks=gt_masks)
+        with torch.autocast(img.device.type, dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+            losses = self.model.forward_train(img, img_metas, gt_rels=gt_rels, gt_bboxes=None, gt_labels=gt_labels,
+                                              gt_masks=gt_masks)
+        losses = {k: v.float() for k, v in losses.items()}
         total = sum(losses.values())          # mmdet _parse_losses: every key containing "loss"
         total.backward()
         self.collectives = self.reducer.finish()

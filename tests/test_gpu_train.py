@@ -31,8 +31,8 @@ def test_train_outputs_match_the_cuda_forward():
     assert rel_err(c2["cls"], cls["cls"]) < 1e-4 and rel_err(m2["mask"], msk["mask"]) < 1e-4
 
 
-@pytest.mark.parametrize("scope", ["relation", "head"])
-def test_training_steps_update_exactly_the_trainable_set(scope):
+@pytest.mark.parametrize("scope,amp", [("relation", None), ("head", None), ("head", torch.bfloat16)])
+def test_training_steps_update_exactly_the_trainable_set(scope, amp):
     from tests.util import ROOT
     import os
     from pairnet_b200.registry import Config, build_detector
@@ -48,7 +48,7 @@ def test_training_steps_update_exactly_the_trainable_set(scope):
     metas = [dict(img_shape=(H, W, 3), batch_input_shape=(H, W))] * 2
     rels, labels, masks = synthetic_targets(2, (H, W), 5, "cuda")
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
-    ts = TrainStep(model, scope=scope, lr=1e-3)
+    ts = TrainStep(model, scope=scope, lr=1e-3, amp_dtype=amp)
     torch.manual_seed(7)
     hist = []
     for _ in range(6):
