@@ -778,7 +778,48 @@ def run_b200(args, rank, world, local):
         barrier(world)
         te = time_steps(e2e_step, args.steps, flush, stream)
         barrier(world)
-        e2e_ms = max_over_ranks(sum(te), world, device)
+        e2e_serial_ms = max_over_ranks(sum(te), world, device)
+
+        # ---- the same public-API step as a user's input pipeline runs it: double-buffered.  The pinned-host -> device copy
+        # of step i+1's images is issued on a copy stream at the start of step i and overlaps step i's forward; every step
+        # still copies its own 25.6 MB of images from pinned host memory and reads its results back to the host, and the
+        # caller synchronises on the results of step i before step i+1 starts.
+        copy_stream = torch.cuda.Stream(device=device)
+        staging = [torch.empty_like(imgs_dev) for _ in range(2)]
+        host_batches = [imgs_host, synthetic_images(PER_GPU_BATCH, 30086 + rank).pin_memory()]
+        ev_copy = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        counter = [0]
+
+        def prefetch(i):
+            bsel = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[bsel])      # the device-side consumer of this staging buffer (step i-2) is done
+                staging[bsel].copy_(host_batches[bsel], non_blocking=True)
+                ev_copy[bsel].record(copy_stream)
+
+        def e2e_pipelined_step():
+            i = counter[0]
+            counter[0] += 1
+            prefetch(i + 1)
+            stream.wait_event(ev_copy[i % 2])
+            static_in.copy_(staging[i % 2], non_blocking=True)   # device-to-device into the graph's static input (8 us)
+            ev_free[i % 2].record(stream)
+            cls, _, sp, op = runner(static_in)
+            for k in res_keys:
+                host_out[k].copy_(cls[k], non_blocking=True)
+            host_out["sub_pos"].copy_(sp, non_blocking=True)
+            host_out["obj_pos"].copy_(op, non_blocking=True)
+            stream.synchronize()
+
+        prefetch(0)
+        for _ in range(3):
+            e2e_pipelined_step()
+        barrier(world)
+        tp_ = time_steps(e2e_pipelined_step, args.steps, flush, stream)
+        torch.cuda.synchronize()
+        barrier(world)
+        e2e_ms = max_over_ranks(sum(tp_), world, device)
         e2e_value = world * PER_GPU_BATCH * args.steps / (e2e_ms * 1e-3)
         clk = clocks.stop()
 
@@ -818,7 +859,13 @@ def run_b200(args, rank, world, local):
                                      "the upstream cuDNN convolutions run single-pass TF32"},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
-                "result": "all_cls_scores (sub,obj,cls,rel,importance) + sub_pos/obj_pos to pinned host; mask tensors stay on device"},
+                "result": "all_cls_scores (sub,obj,cls,rel,importance) + sub_pos/obj_pos to pinned host; mask tensors stay on device",
+                "pipeline": "double-buffered input: the pinned-host -> device copy of step i+1 (copy stream) overlaps the "
+                            "forward of step i; results of step i are synchronised on the host before step i+1 starts; "
+                            "two distinct host batches alternate",
+                "serial": {"value": world * PER_GPU_BATCH * args.steps / (e2e_serial_ms * 1e-3),
+                           "ms_per_step": e2e_serial_ms / args.steps,
+                           "what": "same step with the H2D copy issued on the compute stream (no overlap)"}},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "clocks": clk,
