@@ -112,6 +112,10 @@ PN_API int pn_get_option(int key);
                                     ops) are launched with programmatic stream serialization (under graph capture: programmatic
                                     edges); each waits with griddepcontrol.wait before touching activations, the skinny GEMM
                                     fetches its (static) weights ahead of the wait.  0 = plain serialized launches */
+#define PN_OPT_ENC_BF16X3 17     /* default 1: the pixel-decoder encoder's GEMMs (upstream of the hot path, fed by TF32 cuDNN convolutions)
+                                    run as "3xBF16": raw fp32 activations split into bf16 hi / lo pairs in the SM, weights as
+                                    prepared bf16 hi / lo planes, three tcgen05.mma kind::f16 products (twice the TF32 rate),
+                                    ~1e-5 of the output scale.  0 = 3xTF32 (~1e-6), as everywhere in the head */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

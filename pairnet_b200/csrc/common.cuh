@@ -126,10 +126,12 @@ struct UmmaOperand {
   int t_rows;    // > 0: transposed store C[(m / t_rows) * N + n][m % t_rows] with row pitch ldc (V^T per image)
   int bias_per_row;  // bias indexed by output row (weights as the A operand, e.g. V^T = Wv . X^T)
   int a_is_raw;      // a_hi points to the RAW fp32 A (a_lo unused): the kernel splits it in the SM through TMEM
+  int w_bf16;        // w_hi / w_lo point to bf16 hi / lo planes (launch_split_bf16): the "3xBF16" variant (raw A only)
   // sign/bit-pack epilogue instead of a store (C may be null): see umma::Problem
   uint32_t* bits; int* rowany; int bits_words;
 };
 int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+int launch_split_bf16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);  // n elements -> bf16 planes
 int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t st);
 
 struct LnArgs {
@@ -230,7 +232,7 @@ int launch_level_prep(const float* mem, const float* level_embed, const float* p
 int launch_level_prep_tokens(const float* mem, long long bstride, const float* level_embed, const float* pos, float* x,
                              float* xp, int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_PPN_FUSED_TOPK = 11, OPT_CONV_TC = 12, OPT_UMMA_TMA_STORE = 13, OPT_SINGLE_PASS = 14, OPT_NVTX = 15, OPT_PDL = 16, OPT_COUNT = 17 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_PPN_FUSED_TOPK = 11, OPT_CONV_TC = 12, OPT_UMMA_TMA_STORE = 13, OPT_SINGLE_PASS = 14, OPT_NVTX = 15, OPT_PDL = 16, OPT_ENC_BF16X3 = 17, OPT_COUNT = 18 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);

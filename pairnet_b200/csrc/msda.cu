@@ -193,10 +193,13 @@ static void enc_take(Workspace& ws, EncBuffers& b, size_t M, int ffn, int ldo) {
 
 
 static inline size_t enc_wmax(int ffn, int ldo) { return (size_t)D * D * 2 + (size_t)ldo * D + (size_t)2 * ffn * D; }
-static inline size_t enc_layer_floats(int ffn, int ldo) { return 2 * enc_wmax(ffn, ldo) + (size_t)round_up(ldo, 64); }
+// prepared blob of one layer: [TF32 hi plane | TF32 lo plane | bf16 hi plane | bf16 lo plane | offsets;attention bias]
+// (the bf16 planes of the 3xBF16 GEMM variant take wmax / 2 floats each); both representations are kept so that
+// PN_OPT_ENC_BF16X3 can be flipped without re-preparing
+static inline size_t enc_layer_floats(int ffn, int ldo) { return 3 * enc_wmax(ffn, ldo) + (size_t)round_up(ldo, 64); }
 // TF32 hi/lo splits of one layer's six weight matrices + the concatenated [offsets ; attention] bias
 static int enc_prepare_layer(const PnMsdaEncoderLayer& Lw, float* w_hi, float* w_lo, float* b_ol, int ffn, int ldo,
-                             int n_off, int n_att, cudaStream_t st) {
+                             int n_off, int n_att, cudaStream_t st, float* w16_hi = nullptr, float* w16_lo = nullptr) {
   float* wo_hi = w_hi + (size_t)D * D;            float* wo_lo = w_lo + (size_t)D * D;
   float* wp_hi = wo_hi + (size_t)ldo * D;         float* wp_lo = wo_lo + (size_t)ldo * D;
   float* w1_hi = wp_hi + (size_t)D * D;           float* w1_lo = wp_lo + (size_t)D * D;
@@ -208,6 +211,18 @@ static int enc_prepare_layer(const PnMsdaEncoderLayer& Lw, float* w_hi, float* w
   PN_TRY(launch_split_tf32(Lw.output_proj.w, wp_hi, wp_lo, (size_t)D * D, st));
   PN_TRY(launch_split_tf32(Lw.ffn1.w, w1_hi, w1_lo, (size_t)ffn * D, st));
   PN_TRY(launch_split_tf32(Lw.ffn2.w, w2_hi, w2_lo, (size_t)ffn * D, st));
+  if (w16_hi) {  // the same six matrices as bf16 hi / lo planes, identical element offsets
+    uint16_t* h = reinterpret_cast<uint16_t*>(w16_hi);
+    uint16_t* l = reinterpret_cast<uint16_t*>(w16_lo);
+    const size_t o_wo = (size_t)D * D, o_wp = o_wo + (size_t)ldo * D, o_w1 = o_wp + (size_t)D * D, o_w2 = o_w1 + (size_t)ffn * D;
+    PN_TRY(launch_split_bf16(Lw.value_proj.w, h, l, (size_t)D * D, st));
+    PN_TRY(launch_split_bf16(Lw.sampling_offsets.w, h + o_wo, l + o_wo, (size_t)n_off * D, st));
+    PN_TRY(launch_split_bf16(Lw.attention_weights.w, h + o_wo + (size_t)n_off * D, l + o_wo + (size_t)n_off * D,
+                             (size_t)n_att * D, st));
+    PN_TRY(launch_split_bf16(Lw.output_proj.w, h + o_wp, l + o_wp, (size_t)D * D, st));
+    PN_TRY(launch_split_bf16(Lw.ffn1.w, h + o_w1, l + o_w1, (size_t)ffn * D, st));
+    PN_TRY(launch_split_bf16(Lw.ffn2.w, h + o_w2, l + o_w2, (size_t)ffn * D, st));
+  }
   cudaError_t e = cudaMemcpyAsync(b_ol, Lw.sampling_offsets.b, sizeof(float) * n_off, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(b_ol + n_off, Lw.attention_weights.b, sizeof(float) * n_att, cudaMemcpyDeviceToDevice, st);
@@ -237,8 +252,9 @@ int pn_msda_encoder_prepare(const PnMsdaEncoderWeights* w, void* blob, size_t bl
   const int ldo = (int)round_up(n_off + n_att, 4);
   for (int i = 0; i < w->num_layers; ++i) {
     float* base = reinterpret_cast<float*>(blob) + (size_t)i * enc_layer_floats(ffn, ldo);
-    PN_TRY(enc_prepare_layer(w->layers[i], base, base + enc_wmax(ffn, ldo), base + 2 * enc_wmax(ffn, ldo), ffn, ldo, n_off,
-                             n_att, as_stream(stream)));
+    const size_t wm = enc_wmax(ffn, ldo);
+    PN_TRY(enc_prepare_layer(w->layers[i], base, base + wm, base + 3 * wm, ffn, ldo, n_off, n_att, as_stream(stream),
+                             base + 2 * wm, base + 2 * wm + wm / 2));
   }
   return 0;
 }
@@ -279,6 +295,11 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
   // raw mode: activations enter the tcgen05 GEMM as plain fp32 and are split inside the SM (TMEM), so no
   // producer materialises hi/lo copies; otherwise every producer emits its output pre-split.
   const bool raw = get_option(OPT_UMMA_RAW_A) != 0;
+  // 3xBF16 (umma_gemm.cu, W16 variant): the encoder's six GEMMs per layer on the kind::f16 pipe at twice the TF32 rate,
+  // ~1e-5 of the scale instead of ~1e-6 -- its inputs come from single-pass-TF32 cuDNN convolutions (1e-3 class).
+  // Needs the prepared blob (bf16 weight planes), raw-A mode, tensor cores on and the fp32-parity pass count.
+  const int w16 = (raw && w->prepared && get_option(OPT_ENC_BF16X3) && get_option(OPT_TENSOR_CORES) &&
+                   !get_option(OPT_SINGLE_PASS) && ffn % 64 == 0) ? 1 : 0;
   float* q_raw = b.q_hi;  // raw mode: q = x + pos lives here
   if (raw) {
     PN_TRY(launch_add_rows(x_in, pos, q_raw, B, nq, st));
@@ -296,15 +317,22 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
     float *w_hi_l = b.w_hi, *w_lo_l = b.w_lo, *b_ol_l = b.b_ol;
     if (w->prepared) {
       float* base = reinterpret_cast<float*>(const_cast<void*>(w->prepared)) + (size_t)i * enc_layer_floats(ffn, ldo);
-      w_hi_l = base; w_lo_l = base + enc_wmax(ffn, ldo); b_ol_l = base + 2 * enc_wmax(ffn, ldo);
+      const size_t wm = enc_wmax(ffn, ldo);
+      w_hi_l = base; w_lo_l = base + wm; b_ol_l = base + 3 * wm;
+      if (w16) { w_hi_l = base + 2 * wm; w_lo_l = base + 2 * wm + wm / 2; }
     } else {
       PN_TRY(enc_prepare_layer(Lw, w_hi_l, w_lo_l, b_ol_l, ffn, ldo, n_off, n_att, st));
     }
+    // sub-matrix offsets are in ELEMENTS: fp32 containers (TF32 planes) or 2-byte bf16 (3xBF16 planes)
+    auto at = [&](float* base, size_t elems) -> float* {
+      return w16 ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(base) + elems) : base + elems;
+    };
+    const size_t o_wo = (size_t)D * D, o_wp = o_wo + (size_t)ldo * D, o_w1 = o_wp + (size_t)D * D, o_w2 = o_w1 + (size_t)ffn * D;
     float* wv_hi = w_hi_l;                          float* wv_lo = w_lo_l;
-    float* wo_hi = wv_hi + (size_t)D * D;           float* wo_lo = wv_lo + (size_t)D * D;
-    float* wp_hi = wo_hi + (size_t)ldo * D;         float* wp_lo = wo_lo + (size_t)ldo * D;
-    float* w1_hi = wp_hi + (size_t)D * D;           float* w1_lo = wp_lo + (size_t)D * D;
-    float* w2_hi = w1_hi + (size_t)ffn * D;         float* w2_lo = w1_lo + (size_t)ffn * D;
+    float* wo_hi = at(w_hi_l, o_wo);                float* wo_lo = at(w_lo_l, o_wo);
+    float* wp_hi = at(w_hi_l, o_wp);                float* wp_lo = at(w_lo_l, o_wp);
+    float* w1_hi = at(w_hi_l, o_w1);                float* w1_lo = at(w_lo_l, o_w1);
+    float* w2_hi = at(w_hi_l, o_w2);                float* w2_lo = at(w_lo_l, o_w2);
     {  // value = x Wv^T + bv ; ol = q [Wo;Wa]^T + [bo;ba]
       UmmaOperand o[2] = {{b.x_hi, b.x_lo, D, wv_hi, wv_lo, D, Lw.value_proj.b, b.value, D, Mi, D, D},
                           {b.q_hi, b.q_lo, D, wo_hi, wo_lo, D, b_ol_l, b.ol, ldo, Mi, n_ol, D}};
@@ -312,6 +340,7 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
         o[0].a_hi = x_cur; o[0].a_lo = nullptr; o[0].a_is_raw = 1;
         o[1].a_hi = q_raw; o[1].a_lo = nullptr; o[1].a_is_raw = 1;
       }
+      o[0].w_bf16 = o[1].w_bf16 = w16;
       PN_TRY(launch_umma_gemm(o, 2, 3, st));
     }
     {
@@ -322,6 +351,7 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
     {
       UmmaOperand o{b.att_hi, raw ? nullptr : b.att_lo, D, wp_hi, wp_lo, D, Lw.output_proj.b, b.proj, D, Mi, D, D};
       o.a_is_raw = raw;
+      o.w_bf16 = w16;
       PN_TRY(launch_umma_gemm(&o, 1, 3, st));
       LnArgs n{};
       n.x = b.proj; n.nparts = 1; n.resid = x_cur; n.gamma = Lw.norm[0].gamma; n.beta = Lw.norm[0].beta;
@@ -332,9 +362,11 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
     {
       UmmaOperand o1{b.x1_hi, b.x1_lo, D, w1_hi, w1_lo, D, Lw.ffn1.b, b.h_hi, ffn, Mi, ffn, D, b.h_lo, 1};
       if (raw) { o1.a_hi = b.x1; o1.a_lo = nullptr; o1.a_is_raw = 1; o1.C_lo = nullptr; }  // h stays raw fp32
+      o1.w_bf16 = w16;
       PN_TRY(launch_umma_gemm(&o1, 1, 3, st));
       UmmaOperand o2{b.h_hi, raw ? nullptr : b.h_lo, ffn, w2_hi, w2_lo, ffn, Lw.ffn2.b, b.y, D, Mi, D, ffn};
       o2.a_is_raw = raw;
+      o2.w_bf16 = w16;
       PN_TRY(launch_umma_gemm(&o2, 1, 3, st));
       const bool last = (i + 1 == w->num_layers);
       LnArgs n{};

@@ -92,16 +92,27 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
 // hi = rna_tf32(a), lo = rna_tf32(a - hi) and park both in tensor memory with tcgen05.st; the MMAs then take A
 // from TMEM (tcgen05.mma with a TMEM A operand) and only B (weights, pre-split) from shared memory.  This halves
 // the A bytes moved through HBM/L2 and frees smem for a 4th pipeline stage.
-template <int BN, int NUM_EPI_WARPS, bool A_RAW>
+//
+// W16 = true ("3xBF16", raw-A only): the same fp32-in / fp32-out GEMM on the kind::f16 pipe, which runs at TWICE the TF32
+// rate.  Weights arrive as bf16 hi / lo planes (hi = bf16(w), lo = bf16(w - hi)); a k-block is 64 channels: two raw fp32
+// A sub-tiles (2 x 16 KiB) + one 16 KiB bf16 tile per weight plane = 64 KiB per stage, 3 stages.  The splitter warps turn
+// each raw row into packed bf16 hi / lo pairs (cvt.rn.bf16x2, two elements per 32-bit TMEM column: the same 32 + 32 columns
+// per k-block as the TF32 variant) and the MMA warp issues lo*hi + hi*lo + hi*hi with K = 16 per instruction -- 12
+// instructions per 64 channels instead of 24.  Dropped terms (lo*lo and the third bf16 digit) are 2^-16..2^-17 relative
+// per product: ~1e-5 of the result's scale, used where the INPUTS already carry TF32-level error (the pixel-decoder
+// encoder, fed by cuDNN TF32 convolutions); the head keeps 3xTF32.
+template <int BN, int NUM_EPI_WARPS, bool A_RAW, bool W16 = false>
 __global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? 128 : 0), 1)
 umma_gemm_kernel(const __grid_constant__ Params prm) {
-  constexpr int STAGES = A_RAW ? 4 : Cfg<BN>::STAGES;
+  static_assert(!W16 || A_RAW, "the bf16-split variant takes a raw fp32 A operand");
+  constexpr int STAGES = W16 ? 3 : (A_RAW ? 4 : Cfg<BN>::STAGES);
   constexpr int B_TILE = Cfg<BN>::B_TILE_BYTES;
-  constexpr int STAGE_BYTES = A_RAW ? (A_TILE_BYTES + 2 * B_TILE) : Cfg<BN>::STAGE_BYTES;
+  constexpr int STAGE_BYTES = W16 ? (2 * A_TILE_BYTES + 2 * B_TILE) : (A_RAW ? (A_TILE_BYTES + 2 * B_TILE) : Cfg<BN>::STAGE_BYTES);
   constexpr int TMEM_COLS = A_RAW ? 512 : Cfg<BN>::TMEM_COLS;
   constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES;
-  constexpr int OFF_B_HI = A_RAW ? A_TILE_BYTES : 2 * A_TILE_BYTES;
+  constexpr int OFF_B_HI = W16 ? 2 * A_TILE_BYTES : (A_RAW ? A_TILE_BYTES : 2 * A_TILE_BYTES);
   constexpr int OFF_B_LO = OFF_B_HI + B_TILE;
+  constexpr int KB = W16 ? 64 : BK;  // channels per k-block
   constexpr bool TMA_EPI = (NUM_EPI_WARPS == 4 && BN == 128);
   constexpr int TM_A = 2 * BN;  // A_RAW: TMEM columns [TM_A + set*64, +32) = hi, [+32, +64) = lo  (4 sets -> 512 total)
   static_assert(!A_RAW || BN == 128, "raw-A variant is built for 128x128 tiles");
@@ -165,12 +176,23 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord<BN>(prm, t);
       const Problem& P = prm.p[tc.p];
-      const int num_kb = P.K / BK;
+      const int num_kb = P.K / KB;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        if (W16) {
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+            tma_load_2d(st, &P.a_hi, &full_bar[s], kb * KB, tc.m0);                       // raw A, channels [0, 32)
+            tma_load_2d(st + A_TILE_BYTES, &P.a_hi, &full_bar[s], kb * KB + BK, tc.m0);   // raw A, channels [32, 64)
+            tma_load_2d(st + OFF_B_HI, &P.b_hi, &full_bar[s], kb * KB, tc.n0);            // bf16 planes: 64 channels = 128 B rows
+            tma_load_2d(st + OFF_B_LO, &P.b_lo, &full_bar[s], kb * KB, tc.n0);
+          }
+          __syncwarp();
+          continue;
+        }
         const uint32_t bytes = A_RAW ? (uint32_t)STAGE_BYTES
                                      : ((prm.passes == 3) ? (uint32_t)STAGE_BYTES : (uint32_t)STAGE_BYTES / 2);
         if (elect_one()) {
@@ -196,7 +218,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
     uint32_t it = 0, tile_it = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x, ++tile_it) {
       const TileCoord tc = tile_coord<BN>(prm, t);
-      const int num_kb = prm.p[tc.p].K / BK;
+      const int num_kb = prm.p[tc.p].K / KB;
       const uint32_t acc = tile_it & 1;
       mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -212,7 +234,21 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
           mbar_wait(&a_ready_bar[set], (it / ASETS) & 1);  // splitter has parked hi/lo of this k-block in TMEM
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi_t = tmem_base + TM_A + set * 64, a_lo_t = a_hi_t + 32;
-          if (elect_one()) {
+          if (W16) {
+            if (elect_one()) {
+              const uint32_t idesc16 = make_idesc_bf16(BN);
+#pragma unroll
+              for (int k = 0; k < KB / UMMA_K_BF16; ++k) {  // 16 channels = 8 packed TMEM columns / 32 bytes of the B row
+                const uint64_t koff = (uint64_t)((k * UMMA_K_BF16 * 2) >> 4);
+                const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                umma_bf16_ts(d_tmem, a_lo_t + k * 8, b_hi + koff, idesc16, first);
+                umma_bf16_ts(d_tmem, a_hi_t + k * 8, b_lo + koff, idesc16, 1u);
+                umma_bf16_ts(d_tmem, a_hi_t + k * 8, b_hi + koff, idesc16, 1u);
+              }
+              umma_commit(&empty_bar[s]);
+              umma_commit(&a_free_bar[set]);
+            }
+          } else if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
@@ -433,7 +469,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
     uint32_t it = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord<BN>(prm, t);
-      const int num_kb = prm.p[tc.p].K / BK;
+      const int num_kb = prm.p[tc.p].K / KB;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t set = it % ASETS;
@@ -442,6 +478,32 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* arow = smem + (size_t)s * STAGE_BYTES + OFF_A_HI + r * 128;
         uint32_t hi[32], lo[32];
+        if (W16) {
+          // 64 channels of this row (two swizzled sub-tiles) -> 32 packed bf16 hi pairs + 32 packed lo pairs; the lower
+          // channel of a pair sits in the lower half of the 32-bit TMEM column
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(arow + h * A_TILE_BYTES + ((c ^ (r & 7)) << 4));
+              const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+              hi[h * 16 + c * 2] = h0;
+              hi[h * 16 + c * 2 + 1] = h1;
+              lo[h * 16 + c * 2] = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
+              lo[h * 16 + c * 2 + 1] = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
+            }
+          }
+          tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64, hi);
+          tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64 + 32, lo);
+          tmem_st_wait();
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&a_ready_bar[set]);
+            mbar_arrive(&empty_bar[s]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // logical 16-byte chunk c of the row lives at physical chunk c ^ (r & 7)
           const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
@@ -492,6 +554,17 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+// weights -> bf16 hi / lo planes for the W16 variant: hi = bf16(w), lo = bf16(w - hi)   (round to nearest even)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, uint32_t* __restrict__ hi,
+                                                          uint32_t* __restrict__ lo, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n2; i += (size_t)gridDim.x * 256) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(x) + i);
+    const uint32_t h = pack_bf16x2(v.x, v.y);
+    hi[i] = h;
+    lo[i] = pack_bf16x2(v.x - __uint_as_float(h << 16), v.y - __uint_as_float(h & 0xffff0000u));
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -527,6 +600,21 @@ int make_tmap_2d(CUtensorMap* map, const float* ptr, long long rows, long long c
 }
 static int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld) {
   return make_tmap_2d(map, ptr, rows, cols, ld, BK, BM);
+}
+// bf16 plane [rows, cols] (ld elements): box 64 channels (= 128 B) x 128 rows, SWIZZLE_128B
+static int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  PN_REQUIRE(fn, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  PN_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, PN_ERR_UNSUPPORTED, "umma: bf16 operand must be 16B aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled(bf16) failed (%d)", (int)r);
+  return 0;
 }
 
 }  // namespace umma
@@ -566,6 +654,16 @@ int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream
   return launch_split_tf32_scaled(x, hi, lo, n, 1.0f, st);
 }
 
+int launch_split_bf16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st) {
+  PN_REQUIRE(x && hi && lo && n % 2 == 0, PN_ERR_BAD_ARG, "split_bf16: bad args");
+  PN_REQUIRE((((uintptr_t)x & 7) | ((uintptr_t)hi & 3) | ((uintptr_t)lo & 3)) == 0, PN_ERR_UNSUPPORTED, "split_bf16: alignment");
+  const size_t n2 = n / 2;
+  int blocks = (int)((n2 + 255) / 256);
+  blocks = blocks > 148 * 16 ? 148 * 16 : (blocks < 1 ? 1 : blocks);
+  umma::split_bf16_kernel<<<blocks, 256, 0, st>>>(x, reinterpret_cast<uint32_t*>(hi), reinterpret_cast<uint32_t*>(lo), n2);
+  return check_launch("split_bf16_kernel");
+}
+
 int launch_split_tf32_scaled(const float* x, float* hi, float* lo, size_t n, float scale, cudaStream_t st) {
   PN_REQUIRE(x && hi && lo && n % 4 == 0, PN_ERR_BAD_ARG, "split_tf32: bad args");
   PN_REQUIRE((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, PN_ERR_UNSUPPORTED, "split_tf32: alignment");
@@ -599,9 +697,18 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
                "umma: C must be 16B aligned");
     Problem& p = prm.p[i];
     PN_TRY(make_map(&p.a_hi, o.a_hi, o.M, o.K, o.lda));
-    PN_TRY(make_map(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
-    PN_TRY(make_map(&p.a_lo, (passes == 3 && !o.a_is_raw) ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
-    PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
+    if (o.w_bf16) {
+      // 3xBF16: raw fp32 A, weights as bf16 hi / lo planes (same pointers, 2-byte elements)
+      PN_REQUIRE(o.a_is_raw && passes == 3 && !single && o.K % 64 == 0 && !o.C_lo, PN_ERR_UNSUPPORTED,
+                 "umma: bf16-split weights need a raw A operand, 3 passes and K %% 64 == 0");
+      PN_TRY(make_map(&p.a_lo, o.a_hi, o.M, o.K, o.lda));
+      PN_TRY(make_map_bf16(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
+      PN_TRY(make_map_bf16(&p.b_lo, o.w_lo, o.N, o.K, o.ldw));
+    } else {
+      PN_TRY(make_map(&p.b_hi, o.w_hi, o.N, o.K, o.ldw));
+      PN_TRY(make_map(&p.a_lo, (passes == 3 && !o.a_is_raw) ? o.a_lo : o.a_hi, o.M, o.K, o.lda));
+      PN_TRY(make_map(&p.b_lo, passes == 3 ? o.w_lo : o.w_hi, o.N, o.K, o.ldw));
+    }
     p.tma_store = 0;
     if (!o.bits && o.t_rows <= 0 && get_option(OPT_UMMA_TMA_STORE) && o.ldc % 4 == 0 && ((uintptr_t)o.C & 15) == 0) {
       PN_TRY(make_tmap_2d(&p.c_map, o.C, o.M, o.N, o.ldc, 32, 32));
@@ -634,11 +741,18 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)RAW_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RAW_SMEM_BYTES);
     PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   bool raw = passes == 3;
   for (int i = 0; i < count; ++i) raw = raw && ops[i].a_is_raw;
+  bool w16 = raw;
+  for (int i = 0; i < count; ++i) w16 = w16 && ops[i].w_bf16;
+  for (int i = 0; i < count; ++i)
+    PN_REQUIRE(w16 || !ops[i].w_bf16, PN_ERR_BAD_ARG, "umma: bf16-split and TF32-split problems cannot share a launch");
   bool wide = !raw && get_option(OPT_UMMA_WIDE) != 0;
   for (int i = 0; i < count; ++i) wide = wide && (ops[i].N % 256 == 0);
   const int BN = wide ? 256 : 128;
@@ -647,7 +761,9 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   for (int i = 0; i < count; ++i) prm.total_tiles += cdiv(ops[i].M, BM) * cdiv(ops[i].N, BN);
   const int num_sms = sm_count();
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
-  if (raw && get_option(OPT_UMMA_EPI8))
+  if (w16)
+    umma_gemm_kernel<128, 4, true, true><<<grid, 64 + 32 * 4 + 128, RAW_SMEM_BYTES, st>>>(prm);
+  else if (raw && get_option(OPT_UMMA_EPI8))
     umma_gemm_kernel<128, 8, true><<<grid, 64 + 32 * 8 + 128, RAW_SMEM_BYTES, st>>>(prm);
   else if (raw)
     umma_gemm_kernel<128, 4, true><<<grid, 64 + 32 * 4 + 128, RAW_SMEM_BYTES, st>>>(prm);

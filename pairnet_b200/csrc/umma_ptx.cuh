@@ -132,6 +132,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       : "memory");
 }
 
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two floats -> packed bf16 pair, round to nearest even; `lo` lands in bits [0, 16), `hi` in bits [16, 32)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // round to nearest TF32, ties away from zero -- what cvt.rna.tf32.f32 computes -- as two integer ops: add half a TF32 ulp
 // to the magnitude bits, clear the low 13.  ptxas expands the cvt into ~9 instructions (NaN / Inf selects); this
 // form is bit-identical for every finite input and Inf, and keeps quiet NaNs NaN.

@@ -397,6 +397,39 @@ def test_msda_encoder_native_vs_torch():
     assert rel_err(mf_n, mf_o) < 5e-3
 
 
+def test_msda_encoder_bf16x3_vs_3xtf32():
+    """PN_OPT_ENC_BF16X3 (default on): the encoder's GEMMs as three bf16 products on tcgen05 kind::f16 (raw fp32
+    activations split in the SM, prepared bf16 weight planes) vs the 3xTF32 variant of the same kernel: ~1e-5 of the
+    scale (stated bound 1e-4, two orders below the TF32 convolutions that feed the encoder), at a size that covers
+    ragged M tiles, N = 288 (three n-tiles, the last one partial) and K = 1024."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    m = _pixel_decoder()
+    feats = [_t((2, 256, 72, 100), 41).cuda(), _t((2, 512, 36, 50), 42).cuda(), _t((2, 1024, 18, 25), 43).cuda(),
+             _t((2, 2048, 9, 13), 44).cuda()]
+    assert lib.pn_get_option(nat.PN_OPT_ENC_BF16X3) == 1
+    with torch.no_grad():
+        mf_b, mem_b = m(feats)
+        mf_b, mem_b = mf_b.clone(), [t.clone() for t in mem_b]
+        lib.pn_set_option(nat.PN_OPT_ENC_BF16X3, 0)
+        try:
+            mf_t, mem_t = m(feats)
+        finally:
+            lib.pn_set_option(nat.PN_OPT_ENC_BF16X3, 1)
+        m.encoder_impl = "torch"
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            _, mem_ref = m(feats)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+    for a, b, r in zip(mem_b, mem_t, mem_ref):
+        assert a.shape == b.shape and not torch.equal(a, b)      # the two variants are different arithmetic
+        assert rel_err(a, b) < 1e-4
+        assert rel_err(a, r) < 3e-4 and rel_err(b, r) < 3e-4      # both agree with the fp32 PyTorch encoder
+    assert rel_err(mf_b, mf_t) < 1e-3                             # downstream of a TF32 cuDNN 3x3 convolution
+
+
 @pytest.mark.parametrize("channels_last", [False, True])
 @pytest.mark.parametrize("relu", [False, True])
 def test_group_norm_native(channels_last, relu):
