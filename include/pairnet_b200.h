@@ -177,6 +177,13 @@ PN_API int pn_split_tf32(const float* x, float* hi, float* lo, size_t n, pn_stre
 /* raw-A variant (default in production): x stays plain fp32 and is split inside the SM through TMEM */
 PN_API int pn_linear_tc_rawa(const float* x, const float* w_hi, const float* w_lo, const float* b, float* y,
                              int ldy, int M, int N, int K, pn_stream_t stream);
+/* "3xBF16" form of pn_linear_tc_rawa: y = x W^T + b with fp32 activations in and out, on tcgen05.mma kind::f16 at twice the
+ * TF32 rate.  w_hi / w_lo: bf16 planes of W [N,K] from pn_split_bf16 (hi = bf16(w), lo = bf16(w - hi), bit patterns as
+ * uint16_t); x is split into bf16 hi / lo pairs inside the SM.  Three products (hi*hi + hi*lo + lo*hi): ~1e-5 of the output
+ * scale (3xTF32: ~1e-6).  K % 64 == 0.  Used by the pixel-decoder encoder (PN_OPT_ENC_BF16X3). */
+PN_API int pn_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, pn_stream_t stream);
+PN_API int pn_linear_tc_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* w_lo, const float* b, float* y,
+                        int ldy, int M, int N, int K, pn_stream_t stream);
 PN_API int pn_linear_tc_presplit(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                                  const float* b, float* y, int ldy, int M, int N, int K, int passes,
                                  pn_stream_t stream);

@@ -122,6 +122,8 @@ SIGNATURES = {
     "pn_linear_tc": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
     "pn_split_tf32": (i32, [vp, vp, vp, sz, vp]),
     "pn_linear_tc_rawa": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "pn_split_bf16": (i32, [vp, vp, vp, sz, vp]),
+    "pn_linear_tc_bf16x3": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "pn_linear_tc_presplit": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "pn_add_layernorm": (i32, [vp, vp, vp, vp, vp, i32, vp]),
     "pn_mha_workspace_bytes": (sz, [i32, i32, i32]),

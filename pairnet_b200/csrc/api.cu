@@ -987,6 +987,18 @@ int pn_linear_tc_rawa(const float* x, const float* w_hi, const float* w_lo, cons
   return launch_umma_gemm(&o, 1, 3, as_stream(stream));
 }
 
+int pn_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, size_t n, pn_stream_t stream) {
+  return launch_split_bf16(x, hi, lo, n, as_stream(stream));
+}
+
+int pn_linear_tc_bf16x3(const float* x, const uint16_t* w_hi, const uint16_t* w_lo, const float* b, float* y, int ldy,
+                        int M, int N, int K, pn_stream_t stream) {
+  UmmaOperand o{x, nullptr, K, reinterpret_cast<const float*>(w_hi), reinterpret_cast<const float*>(w_lo), K, b, y, ldy, M, N, K};
+  o.a_is_raw = 1;
+  o.w_bf16 = 1;
+  return launch_umma_gemm(&o, 1, 3, as_stream(stream));
+}
+
 int pn_linear_tc_presplit(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* b,
                           float* y, int ldy, int M, int N, int K, int passes, pn_stream_t stream) {
   UmmaOperand o{x_hi, x_lo, K, w_hi, w_lo, K, b, y, ldy, M, N, K};

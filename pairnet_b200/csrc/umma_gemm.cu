@@ -102,7 +102,7 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
 // per product: ~1e-5 of the result's scale, used where the INPUTS already carry TF32-level error (the pixel-decoder
 // encoder, fed by cuDNN TF32 convolutions); the head keeps 3xTF32.
 template <int BN, int NUM_EPI_WARPS, bool A_RAW, bool W16 = false>
-__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? 128 : 0), 1)
+__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? (W16 ? 256 : 128) : 0), 1)
 umma_gemm_kernel(const __grid_constant__ Params prm) {
   static_assert(!W16 || A_RAW, "the bf16-split variant takes a raw fp32 A operand");
   constexpr int STAGES = W16 ? 3 : (A_RAW ? 4 : Cfg<BN>::STAGES);
@@ -147,14 +147,14 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], A_RAW ? 5 : 1);  // MMA commit (+ the 4 splitter warps that read the raw A tile)
+      mbar_init(&empty_bar[s], A_RAW ? (W16 ? 9 : 5) : 1);  // MMA commit (+ the 4 / 8 splitter warps that read the raw A tile)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     for (int a = 0; a < ASETS; ++a) {
-      mbar_init(&a_ready_bar[a], 4);
+      mbar_init(&a_ready_bar[a], W16 ? 8 : 4);
       mbar_init(&a_free_bar[a], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -466,6 +466,12 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    // W16: TWO splitter groups of four warps, each takes one 32-channel half of every k-block.  One warp per scheduler
+    // turns a 64-channel k-block around in ~0.9 us (wait -> LDS -> ~200 ALU -> tcgen05.st -> wait::st -> arrive: a
+    // latency chain, measured) while its MMAs take 0.56 us; halving the work per warp puts the splitters back under the
+    // tensor pipe.  (Alternating k-blocks between the groups instead would make each group skip mbarrier phases of the
+    // 3-deep ring: a parity wait cannot tell phase n from phase n + 2.)
+    const int grp = (warp - (2 + NUM_EPI_WARPS)) >> 2;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord<BN>(prm, t);
@@ -481,20 +487,18 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
         if (W16) {
           // 64 channels of this row (two swizzled sub-tiles) -> 32 packed bf16 hi pairs + 32 packed lo pairs; the lower
           // channel of a pair sits in the lower half of the 32-bit TMEM column
+          // this group's half: channels [32 grp, 32 grp + 32) = sub-tile grp -> 16 hi + 16 lo columns
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 v = *reinterpret_cast<const float4*>(arow + h * A_TILE_BYTES + ((c ^ (r & 7)) << 4));
-              const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
-              hi[h * 16 + c * 2] = h0;
-              hi[h * 16 + c * 2 + 1] = h1;
-              lo[h * 16 + c * 2] = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
-              lo[h * 16 + c * 2 + 1] = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
-            }
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + grp * A_TILE_BYTES + ((c ^ (r & 7)) << 4));
+            const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+            hi[c * 2] = h0;
+            hi[c * 2 + 1] = h1;
+            lo[c * 2] = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
+            lo[c * 2 + 1] = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
           }
-          tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64, hi);
-          tmem_st_32x32b_x32(tmem_base + lane_addr + TM_A + set * 64 + 32, lo);
+          tmem_st_32x32b_x16(tmem_base + lane_addr + TM_A + set * 64 + grp * 16, hi);
+          tmem_st_32x32b_x16(tmem_base + lane_addr + TM_A + set * 64 + 32 + grp * 16, lo);
           tmem_st_wait();
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -762,7 +766,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   const int num_sms = sm_count();
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
   if (w16)
-    umma_gemm_kernel<128, 4, true, true><<<grid, 64 + 32 * 4 + 128, RAW_SMEM_BYTES, st>>>(prm);
+    umma_gemm_kernel<128, 4, true, true><<<grid, 64 + 32 * 4 + 256, RAW_SMEM_BYTES, st>>>(prm);
   else if (raw && get_option(OPT_UMMA_EPI8))
     umma_gemm_kernel<128, 8, true><<<grid, 64 + 32 * 8 + 128, RAW_SMEM_BYTES, st>>>(prm);
   else if (raw)

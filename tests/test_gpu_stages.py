@@ -356,6 +356,31 @@ def test_linear_tc_3xtf32_matches_fp32(M, N, K):
     assert 1e-5 < e1 < 5e-3  # really went through TF32 tensor cores
 
 
+@pytest.mark.parametrize("M,N,K", [(1500, 256, 256), (4097, 288, 256), (2100, 1024, 256), (1111, 256, 1024), (300, 64, 64)])
+def test_linear_tc_bf16x3(M, N, K):
+    """`pn_linear_tc_bf16x3`: fp32 in / out GEMM as three bf16 products on tcgen05 kind::f16 (hi*hi + hi*lo + lo*hi).
+    Error model: dropped lo*lo and third-digit terms, 2^-16..2^-17 per product -> bound 5e-5 of the output scale; the
+    bf16 split itself is checked exactly (hi = bf16(w), lo = bf16(w - hi))."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    st = torch.cuda.current_stream().cuda_stream
+    x, w, b = _t((M, K), 30).cuda(), _t((N, K), 31, 0.1).cuda(), _t((N,), 32).cuda()
+    wh = torch.empty((N, K), dtype=torch.bfloat16, device="cuda")
+    wl = torch.empty((N, K), dtype=torch.bfloat16, device="cuda")
+    nat.check(lib.pn_split_bf16(w.data_ptr(), wh.data_ptr(), wl.data_ptr(), w.numel(), st), "pn_split_bf16")
+    assert torch.equal(wh, w.to(torch.bfloat16)) and torch.equal(wl, (w - wh.float()).to(torch.bfloat16))
+    y = torch.empty((M, N), device="cuda")
+    nat.check(lib.pn_linear_tc_bf16x3(x.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(), y.data_ptr(), N, M, N, K,
+                                      st), "pn_linear_tc_bf16x3")
+    ref = x.double() @ w.double().t() + b.double()
+    err = rel_err(y, ref)
+    assert 1e-7 < err < 5e-5, err
+    # the model of the arithmetic: exact products of the bf16 digits, fp32-accumulated
+    xh = x.to(torch.bfloat16).double(); xl = (x - xh.float()).to(torch.bfloat16).double()
+    model = xh @ wh.double().t() + xh @ wl.double().t() + xl @ wh.double().t() + b.double()
+    assert rel_err(y, model) < 5e-6
+
+
 def _pixel_decoder(seed=3):
     import os
     from pairnet_b200.registry import Config, PLUGIN_LAYERS
