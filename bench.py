@@ -56,6 +56,13 @@ def parse_args():
     return ap.parse_args()
 
 
+# DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/r02t_ncu_metrics.md)
+NCU_TRAFFIC_BF16X3 = 167.0e6
+NCU_TRAFFIC_BF16X3_SOURCE = ("ncu --set full r02t capture (profiles/r02t_ncu_metrics.md, umma_gemm_bf16x3_ffn1): dram read + write "
+                             "167 MB per launch, below the 226 MB algorithmic (part of C is still in L2 at kernel end); "
+                             "720 MB cross the L2 -> SM crossbar (l1tex__m_xbar2l1tex_read_bytes)")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -225,51 +232,74 @@ def time_steps(step_fn, steps, flush_buf, stream):
 
 
 def dominant_kernel_roofline(model, device, pk):
-    """Dominant hand-written kernel: `umma_gemm_kernel` (tcgen05 kind::tf32, 3xTF32 split operands, TMA-staged
-    tiles, TMEM accumulators) on the K/V projection of the 100x167 memory level: M = 2*16700 tokens,
-    N = 512 (K and V of one layer), K = 256 -> algorithmic flops per launch = 2*M*512*256 (the tensor pipe
-    executes 3x that: lo*hi + hi*lo + hi*hi).  Timed alone (operands pre-split), L2 flushed between launches."""
+    """Dominant hand-written kernel of the step: `umma_gemm_kernel<128,4,raw-A,W16>` -- the "3xBF16" tcgen05 GEMM of the
+    pixel-decoder encoder (36 of the 45 tcgen05-GEMM launches of one forward) -- on its largest problem, the FFN1 linear
+    M = 2*21950 tokens, N = 1024, K = 256: algorithmic flops per launch = 2*M*N*K (the tensor pipe executes 3x that on
+    kind::f16: lo*hi + hi*lo + hi*hi).  Timed alone, L2 flushed between launches.  The 3xTF32 variant of the same kernel
+    (the head's K/V projections, fp32 parity) is reported next to it on the round-1/2 problem (M=33400, N=512, K=256)."""
     from pairnet_b200 import _native as nat
     lib = nat.load()
-    M, d = PER_GPU_BATCH * 100 * 167, 256
     st = torch.cuda.current_stream().cuda_stream
-    x = torch.randn(M, d, device=device)
-    w = torch.randn(2 * d, d, device=device) * 0.05
-    b = torch.zeros(2 * d, device=device)
-    y = torch.empty(M, 2 * d, device=device)
-    xh, xl, wh, wl = torch.empty_like(x), torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
-    nat.check(lib.pn_split_tf32(x.data_ptr(), xh.data_ptr(), xl.data_ptr(), x.numel(), st), "pn_split_tf32")
-    nat.check(lib.pn_split_tf32(w.data_ptr(), wh.data_ptr(), wl.data_ptr(), w.numel(), st), "pn_split_tf32")
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
 
-    def launch():  # production variant: A enters raw and is split hi/lo inside the SM through TMEM
-        nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(), y.data_ptr(), 2 * d,
-                                        M, 2 * d, d, st), "pn_linear_tc_rawa")
-    for _ in range(3):
-        launch()
-    ts = time_steps(launch, 10, flush, torch.cuda.current_stream())
-    ms = statistics.mean(ts)
-    flops = 2.0 * M * (2 * d) * d
+    def timed(fn, n=10):
+        for _ in range(3):
+            fn()
+        return statistics.mean(time_steps(fn, n, flush, torch.cuda.current_stream()))
+
+    # ---- 3xBF16, encoder FFN1
+    M, N, K = PER_GPU_BATCH * 21950, 1024, 256
+    x = torch.randn(M, K, device=device)
+    w = torch.randn(N, K, device=device) * 0.05
+    b = torch.zeros(N, device=device)
+    y = torch.empty(M, N, device=device)
+    w16h = torch.empty((N, K), dtype=torch.bfloat16, device=device)
+    w16l = torch.empty_like(w16h)
+    nat.check(lib.pn_split_bf16(w.data_ptr(), w16h.data_ptr(), w16l.data_ptr(), w.numel(), st), "pn_split_bf16")
+    ms = timed(lambda: nat.check(lib.pn_linear_tc_bf16x3(x.data_ptr(), w16h.data_ptr(), w16l.data_ptr(), b.data_ptr(),
+                                                         y.data_ptr(), N, M, N, K, st), "pn_linear_tc_bf16x3"))
+    flops = 2.0 * M * N * K
     achieved = flops / (ms * 1e-3) / 1e12
-    # the FFMA kernel this replaced, same problem, for reference
-    def launch_ffma():
-        nat.check(lib.pn_linear(x.data_ptr(), d, w.data_ptr(), b.data_ptr(), None, y.data_ptr(), 2 * d, M, 2 * d, d, 0,
-                                st), "pn_linear")
-    launch_ffma()
-    ms_ffma = statistics.mean(time_steps(launch_ffma, 5, flush, torch.cuda.current_stream()))
-    alg_bytes = 4.0 * (M * d + 2 * 2 * d * d + M * 2 * d)  # A (raw fp32), W hi+lo, C
-    return {"bound": "tensor", "kernel": "umma_gemm_kernel<128,4,raw-A>: tcgen05.mma kind::tf32 x3 (fp32-parity hi/lo split, A "
-                                         "split in-SM through TMEM, TMA-store epilogue), K/V-projection problem of the "
-                                         "100x167 level, M=33400 N=512 K=256",
+    alg_bytes = 4.0 * (M * K + M * N) + 2.0 * 2 * N * K   # A (raw fp32) + C (fp32) + W bf16 hi / lo planes
+    tiles = ((M + 127) // 128) * (N // 128)
+    smem_fill = tiles * (K // 64) * 65536.0                # bytes TMA moves from L2 into shared memory per launch
+    del x, w, y
+
+    # ---- 3xTF32, head K/V projection (the previous rounds' roofline problem)
+    M2, d = PER_GPU_BATCH * 100 * 167, 256
+    x2 = torch.randn(M2, d, device=device)
+    w2 = torch.randn(2 * d, d, device=device) * 0.05
+    b2 = torch.zeros(2 * d, device=device)
+    y2 = torch.empty(M2, 2 * d, device=device)
+    wh, wl = torch.empty_like(w2), torch.empty_like(w2)
+    nat.check(lib.pn_split_tf32(w2.data_ptr(), wh.data_ptr(), wl.data_ptr(), w2.numel(), st), "pn_split_tf32")
+    ms_tf32 = timed(lambda: nat.check(lib.pn_linear_tc_rawa(x2.data_ptr(), wh.data_ptr(), wl.data_ptr(), b2.data_ptr(),
+                                                            y2.data_ptr(), 2 * d, M2, 2 * d, d, st), "pn_linear_tc_rawa"))
+    ms_ffma = timed(lambda: nat.check(lib.pn_linear(x2.data_ptr(), d, w2.data_ptr(), b2.data_ptr(), None, y2.data_ptr(), 2 * d,
+                                                    M2, 2 * d, d, 0, st), "pn_linear"), n=5)
+    flops2 = 2.0 * M2 * (2 * d) * d
+    ach2 = flops2 / (ms_tf32 * 1e-3) / 1e12
+    return {"bound": "tensor",
+            "kernel": "umma_gemm_kernel<128,4,raw-A,W16>: tcgen05.mma kind::f16 x3 ('3xBF16': raw fp32 A split into packed bf16 "
+                      "hi/lo pairs in the SM through TMEM, prepared bf16 weight planes, TMA-store epilogue), pixel-decoder "
+                      "encoder FFN1, M=43900 N=1024 K=256",
             "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": 47.6e6, "traffic_source": "ncu --set full r02l capture (profiles/r02l_ncu_metrics.md, umma_gemm_kv): "
-                                                  "dram read + write 47.6 MB per launch (C partly still in L2 at kernel end)",
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "ms_per_launch": ms, "flops_per_launch": flops, "tensor_pipe_flops_per_launch": 3 * flops,
-            "peak_source": pk["source"], "ffma_kernel_ms_same_problem": ms_ffma,
-            "note": "3xTF32 = 3 tensor-pipe passes at the TF32 rate (half the bf16 rate): the ceiling for this "
-                    "fp32-parity kernel is peak/6 of the dense bf16 figure; achieved/(peak/6) is the useful fraction",
-            "frac_of_3xtf32_ceiling": achieved / (pk["bf16_tflops"] / 6.0)}
+            "traffic": NCU_TRAFFIC_BF16X3, "traffic_source": NCU_TRAFFIC_BF16X3_SOURCE,
+            "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms, "flops_per_launch": flops,
+            "tensor_pipe_flops_per_launch": 3 * flops, "peak_source": pk["source"],
+            "frac_of_3xbf16_ceiling": achieved / (pk["bf16_tflops"] / 3.0),
+            "l2_to_smem_bytes_per_launch": smem_fill, "l2_to_smem_tbs": smem_fill / (ms * 1e-3) / 1e12,
+            "note": "3 tensor-pipe products per algorithmic flop at the bf16 rate: the tensor ceiling of this fp32-in/fp32-out "
+                    "kernel is peak/3.  What actually bounds it is the L2 -> shared-memory fill: every 128x128 tile re-reads its "
+                    "A rows (raw fp32) and weight planes, l2_to_smem_tbs is close to the ~12 TB/s LTS cap the microarchitecture "
+                    "guide measures (6300 B/clk); the 3xTF32 variant moves 1.5x the bytes per flop and is 1.2-1.36x slower",
+            "tf32_variant": {"kernel": "umma_gemm_kernel<128,4,raw-A>: kind::tf32 x3 (fp32 parity), head K/V projection of the "
+                                       "100x167 level, M=33400 N=512 K=256",
+                             "achieved": ach2, "frac": ach2 / pk["bf16_tflops"], "ms_per_launch": ms_tf32,
+                             "frac_of_3xtf32_ceiling": ach2 / (pk["bf16_tflops"] / 6.0), "flops_per_launch": flops2,
+                             "traffic": 47.6e6, "traffic_source": "ncu --set full r02l capture (profiles/r02l_ncu_metrics.md, "
+                                                                   "umma_gemm_kv)",
+                             "ffma_kernel_ms_same_problem": ms_ffma}}
 
 
 def ppn_microbench(device, pk):

@@ -16,6 +16,16 @@ if which in ('gemm', 'all'):
     for _ in range(3):
         nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(), y.data_ptr(), N, M, N, K, st), "rawa")
     torch.cuda.synchronize()
+if which in ('gemm16', 'gemm16_ffn2'):
+    M, N, K = (43900, 1024, 256) if which == 'gemm16' else (43900, 256, 1024)
+    x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * 0.05; b = torch.zeros(N, device=dev)
+    wh = torch.empty((N, K), dtype=torch.bfloat16, device=dev); wl = torch.empty_like(wh); y = torch.empty(M, N, device=dev)
+    nat.check(lib.pn_split_bf16(w.data_ptr(), wh.data_ptr(), wl.data_ptr(), w.numel(), st), "split16")
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        flush.add_(1.0)
+        nat.check(lib.pn_linear_tc_bf16x3(x.data_ptr(), wh.data_ptr(), wl.data_ptr(), b.data_ptr(), y.data_ptr(), N, M, N, K, st), "b16")
+    torch.cuda.synchronize()
 if which in ('fa', 'all'):
     B, Nq, Nk = 2, 100, 16700
     q = torch.randn(B, Nq, 256, device=dev) * 0.3; k = torch.randn(B, Nk, 256, device=dev) * 0.3; v = torch.randn(B, Nk, 256, device=dev)
