@@ -299,7 +299,7 @@ int pn_msda_encoder_forward(const PnMsdaEncoderWeights* w, const float* x_in, co
   // ~1e-5 of the scale instead of ~1e-6 -- its inputs come from single-pass-TF32 cuDNN convolutions (1e-3 class).
   // Needs the prepared blob (bf16 weight planes), raw-A mode, tensor cores on and the fp32-parity pass count.
   const int w16 = (raw && w->prepared && get_option(OPT_ENC_BF16X3) && get_option(OPT_TENSOR_CORES) &&
-                   !get_option(OPT_SINGLE_PASS) && ffn % 64 == 0) ? 1 : 0;
+                   !get_option(OPT_SINGLE_PASS) && get_option(OPT_UMMA_TMA_STORE) && ffn % 64 == 0) ? 1 : 0;
   float* q_raw = b.q_hi;  // raw mode: q = x + pos lives here
   if (raw) {
     PN_TRY(launch_add_rows(x_in, pos, q_raw, B, nq, st));

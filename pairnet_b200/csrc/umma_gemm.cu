@@ -102,7 +102,7 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& prm, int t) {
 // per product: ~1e-5 of the result's scale, used where the INPUTS already carry TF32-level error (the pixel-decoder
 // encoder, fed by cuDNN TF32 convolutions); the head keeps 3xTF32.
 template <int BN, int NUM_EPI_WARPS, bool A_RAW, bool W16 = false>
-__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? (W16 ? 256 : 128) : 0), 1)
+__global__ void __launch_bounds__(64 + 32 * NUM_EPI_WARPS + (A_RAW ? (W16 ? 288 : 128) : 0), 1)
 umma_gemm_kernel(const __grid_constant__ Params prm) {
   static_assert(!W16 || A_RAW, "the bf16-split variant takes a raw fp32 A operand");
   constexpr int STAGES = W16 ? 3 : (A_RAW ? 4 : Cfg<BN>::STAGES);
@@ -113,28 +113,41 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   constexpr int OFF_B_HI = W16 ? 2 * A_TILE_BYTES : (A_RAW ? A_TILE_BYTES : 2 * A_TILE_BYTES);
   constexpr int OFF_B_LO = OFF_B_HI + B_TILE;
   constexpr int KB = W16 ? 64 : BK;  // channels per k-block
-  constexpr bool TMA_EPI = (NUM_EPI_WARPS == 4 && BN == 128);
+  // TMA-store epilogue: one staging tile per epilogue warp.  W16 runs EIGHT epilogue warps (two per TMEM lane quadrant, 64
+  // columns each -- the ncu role profile of the 4-warp version showed them 78 % busy with the splitters starved behind
+  // them on the K = 256 problems); their four extra tiles take the place of the bias staging area, the bias is read
+  // from global memory instead (one broadcast 16-byte request per 4 columns).
+  constexpr bool TMA_EPI = (BN == 128 && (NUM_EPI_WARPS == 4 || W16));
+  constexpr int EPI_BYTES = W16 ? NUM_EPI_WARPS * EPI_TILE_BYTES : EPI_STAGE_BYTES;
+  static_assert(!W16 || NUM_EPI_WARPS == 8, "the bf16-split variant is built for 8 epilogue warps");
   constexpr int TM_A = 2 * BN;  // A_RAW: TMEM columns [TM_A + set*64, +32) = hi, [+32, +64) = lo  (4 sets -> 512 total)
   static_assert(!A_RAW || BN == 128, "raw-A variant is built for 128x128 tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;  // [4 warps][32 rows x 128 B], 1024-aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   constexpr int ASETS = 4;                        // TMEM A staging sets (hi 32 + lo 32 columns each)
   uint64_t* a_ready_bar = tmem_empty_bar + 2;     // [ASETS]  splitter -> MMA   (A_RAW)
   uint64_t* a_free_bar = a_ready_bar + ASETS;     // [ASETS]  MMA -> splitter   (A_RAW)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_free_bar + ASETS);
-  float* bias_s = reinterpret_cast<float*>(epi_stage + EPI_STAGE_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]
+  // W16: the weight tiles of a stage have their own barrier pair.  The raw A tiles are released by the SPLITTERS (they are
+  // the only readers), the weight tiles by the MMA commit, and a second producer warp refills them independently: the A
+  // round trip (TMA latency + split) no longer contains the MMA time, which is what kept the 3-deep ring from covering
+  // the L2 latency (measured 0.9 us per 64-channel k-block against 0.56 us of MMAs).
+  uint64_t* fullB_bar = a_free_bar + ASETS;       // [STAGES]
+  uint64_t* emptyB_bar = fullB_bar + STAGES;      // [STAGES]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(emptyB_bar + STAGES);
+  static_assert((2 * 4 + 4 + 2 * ASETS + 2 * 4) * 8 + 4 <= 256, "barrier block");
+  float* bias_s = reinterpret_cast<float*>(epi_stage + EPI_BYTES + 256);  // [MAX_PROBLEMS][BIAS_MAX]  (not W16)
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const bool is_epi = warp >= 2 && warp < 2 + NUM_EPI_WARPS;
   // (Not a PDL kernel: launching the persistent tcgen05 kernels with programmatic serialization, or letting them trigger
   // their dependents early, made the pixel-decoder encoder 0.2 ms SLOWER on B200 -- measured, scratch/pdl_ab.py; the
   // attribute is kept for the microsecond-scale kernels of the query-side chain only.)
-  if (is_epi) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
+  if (is_epi && !W16) {  // epilogue warps stage the bias vectors (zeros when absent / beyond N)
     for (int i = threadIdx.x - 64; i < MAX_PROBLEMS * BIAS_MAX; i += 32 * NUM_EPI_WARPS) {
       const int pi = i / BIAS_MAX, n = i % BIAS_MAX;
       float bv = 0.f;
@@ -147,7 +160,9 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], A_RAW ? (W16 ? 9 : 5) : 1);  // MMA commit (+ the 4 / 8 splitter warps that read the raw A tile)
+      mbar_init(&empty_bar[s], A_RAW ? (W16 ? 8 : 5) : 1);  // MMA commit (+ the 4 splitter warps that read the raw A tile); W16: the 8 splitter warps only
+      mbar_init(&fullB_bar[s], 1);
+      mbar_init(&emptyB_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -184,11 +199,9 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
         if (W16) {
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+            mbar_expect_tx(&full_bar[s], (uint32_t)(2 * A_TILE_BYTES));
             tma_load_2d(st, &P.a_hi, &full_bar[s], kb * KB, tc.m0);                       // raw A, channels [0, 32)
             tma_load_2d(st + A_TILE_BYTES, &P.a_hi, &full_bar[s], kb * KB + BK, tc.m0);   // raw A, channels [32, 64)
-            tma_load_2d(st + OFF_B_HI, &P.b_hi, &full_bar[s], kb * KB, tc.n0);            // bf16 planes: 64 channels = 128 B rows
-            tma_load_2d(st + OFF_B_LO, &P.b_lo, &full_bar[s], kb * KB, tc.n0);
           }
           __syncwarp();
           continue;
@@ -212,6 +225,25 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
         __syncwarp();
       }
     }
+  } else if (W16 && warp == 2 + NUM_EPI_WARPS + 8) {
+    // ===== weight-tile producer (W16): bf16 hi / lo planes, 64 channels = 128-byte rows
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < prm.total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord<BN>(prm, t);
+      const Problem& P = prm.p[tc.p];
+      const int num_kb = P.K / KB;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&emptyB_bar[s], ((it / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(&fullB_bar[s], (uint32_t)(2 * B_TILE));
+          tma_load_2d(st + OFF_B_HI, &P.b_hi, &fullB_bar[s], kb * KB, tc.n0);
+          tma_load_2d(st + OFF_B_LO, &P.b_lo, &fullB_bar[s], kb * KB, tc.n0);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
     const uint32_t idesc = make_idesc(BN);
@@ -226,7 +258,7 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(W16 ? &fullB_bar[s] : &full_bar[s], ph);
         const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t b_hi = make_smem_desc(st + OFF_B_HI), b_lo = make_smem_desc(st + OFF_B_LO);
         if (A_RAW) {
@@ -245,8 +277,8 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
                 umma_bf16_ts(d_tmem, a_hi_t + k * 8, b_lo + koff, idesc16, 1u);
                 umma_bf16_ts(d_tmem, a_hi_t + k * 8, b_hi + koff, idesc16, 1u);
               }
-              umma_commit(&empty_bar[s]);
-              umma_commit(&a_free_bar[set]);
+              umma_commit(&emptyB_bar[s]);     // weight tiles of this stage
+              umma_commit(&a_free_bar[set]);   // TMEM A set
             }
           } else if (elect_one()) {
 #pragma unroll
@@ -375,7 +407,15 @@ umma_gemm_kernel(const __grid_constant__ Params prm) {
           if (tc.m0 + quad * 32 >= P.M || n0 + c0 >= P.N) continue;  // warp-uniform
           uint8_t* sb = epi_stage + (size_t)(warp - 2) * EPI_TILE_BYTES;
           float o[32];
-          if (P.bias_per_row) {
+          if (W16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = (P.bias && n0 + c0 + j < P.N) ? __ldg(reinterpret_cast<const float4*>(P.bias + n0 + c0 + j))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+            }
+          } else if (P.bias_per_row) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + bias_row;
           } else {
@@ -719,6 +759,10 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
       if (o.C_lo && !single) PN_TRY(make_tmap_2d(&p.clo_map, o.C_lo, o.M, o.N, o.ldc, 32, 32));
       p.tma_store = 1;
     }
+    // the W16 kernel has no bias staging in smem and only the TMA-store epilogue
+    PN_REQUIRE(!o.w_bf16 || (p.tma_store && !o.bias_per_row && !o.bits && o.t_rows <= 0 && ((uintptr_t)o.bias & 15) == 0),
+               PN_ERR_UNSUPPORTED, "umma: the bf16-split variant needs the TMA-store epilogue (16B-aligned row-major C and "
+               "bias, PN_OPT_UMMA_TMA_STORE = 1)");
     p.bias = o.bias; p.C = o.C; p.M = o.M; p.N = o.N; p.K = o.K; p.ldc = o.ldc;
     p.C_lo = single ? nullptr : o.C_lo; p.relu = o.relu; p.t_rows = o.t_rows; p.bias_per_row = o.bias_per_row;
     p.bits = o.bits; p.rowany = o.rowany; p.bits_words = o.bits_words;
@@ -746,7 +790,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
       e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)RAW_SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(umma_gemm_kernel<128, 8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)RAW_SMEM_BYTES);
     PN_REQUIRE(e == cudaSuccess, (int)e, "umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -766,7 +810,7 @@ int launch_umma_gemm(const UmmaOperand* ops, int count, int passes, cudaStream_t
   const int num_sms = sm_count();
   const int grid = prm.total_tiles < num_sms ? prm.total_tiles : num_sms;
   if (w16)
-    umma_gemm_kernel<128, 4, true, true><<<grid, 64 + 32 * 4 + 256, RAW_SMEM_BYTES, st>>>(prm);
+    umma_gemm_kernel<128, 8, true, true><<<grid, 64 + 32 * 8 + 288, RAW_SMEM_BYTES, st>>>(prm);
   else if (raw && get_option(OPT_UMMA_EPI8))
     umma_gemm_kernel<128, 8, true><<<grid, 64 + 32 * 8 + 128, RAW_SMEM_BYTES, st>>>(prm);
   else if (raw)
