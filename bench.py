@@ -585,8 +585,8 @@ def e2e_simple_test(model, imgs_host, device, flush, stream, steps):
 def config4_head_bench(device, flush, stream):
     """BASELINE config 4's HEAD shapes (200 object / 200 relation queries, 1024x1024 input -> mask_features 256x256,
     memories 32^2 / 64^2 / 128^2, one image per GPU): the hot path alone on synthetic pixel-decoder outputs, in the
-    fp32-parity arithmetic of config 2 (3xTF32) -- the Swin-L backbone and a bf16 arithmetic path are not built, so this
-    is the extrapolated config's head only, labelled as such."""
+    fp32-parity arithmetic of config 2 (3xTF32): the extrapolated config's head only (`config4_e2e_bench` runs the whole
+    config)."""
     from pairnet_b200.registry import Config, build_head
     cfg = Config.fromfile(os.path.join(ROOT, "configs", "pairnet_r50_b200.py"), import_custom_modules=False).model.bbox_head
     cfg["pixel_decoder"] = None
@@ -605,7 +605,7 @@ def config4_head_bench(device, flush, stream):
     return {"what": "CrossHead2 hot path at BASELINE config 4's head shapes: 200/200 queries, 1024x1024 input "
                     "(mask_features 256x256; 1 024 / 4 096 / 16 384 memory tokens), 1 image per GPU, eager launches",
             "ms_per_image": ms, "images_per_sec_per_gpu": 1e3 / ms, "launches": head.last_launch_count,
-            "dtype": "fp32 (3xTF32); bf16 path and Swin-L backbone not built -> extrapolated config, head only"}
+            "dtype": "fp32 (3xTF32), head only; the whole config (Swin-L, bf16-class arithmetic) is `config4_e2e`"}
 
 
 def config4_e2e_bench(device, flush, stream):

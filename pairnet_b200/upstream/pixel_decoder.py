@@ -401,13 +401,29 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 and lib.pn_get_option(nat.PN_OPT_MASK_TC) != 0):
             # the head's tensor-core mask path consumes mask_features token-major: keep the map channels_last
             # (same values, logical NCHW shape) -- plain [B*HW,256] x [256,256]^T GEMM, activations split in the SM
-            wsp = self._scratch("_mf_ws", 2 * cout * Cc * 4, x.device)
-            wh, wl = wsp.data_ptr(), wsp.data_ptr() + cout * Cc * 4
-            nat.check(lib.pn_split_tf32(conv.weight.data_ptr(), wh, wl, cout * Cc, stream), "pn_split_tf32")
+            # static weights: TF32 and bf16 hi / lo planes are split once per weight version
+            bf16x3 = (lib.pn_get_option(nat.PN_OPT_ENC_BF16X3) != 0 and lib.pn_get_option(nat.PN_OPT_SINGLE_PASS) == 0
+                      and lib.pn_get_option(nat.PN_OPT_UMMA_TMA_STORE) != 0 and Cc % 64 == 0)
+            key = (conv.weight.data_ptr(), conv.weight._version, str(x.device))
+            cache = self.__dict__.get("_mf_split")
+            if cache is None or cache[0] != key:
+                blob = torch.empty(3 * cout * Cc, dtype=torch.float32, device=x.device)   # [tf32 hi | tf32 lo | bf16 hi, lo]
+                p0 = blob.data_ptr()
+                nat.check(lib.pn_split_tf32(conv.weight.data_ptr(), p0, p0 + cout * Cc * 4, cout * Cc, stream), "pn_split_tf32")
+                nat.check(lib.pn_split_bf16(conv.weight.data_ptr(), p0 + 2 * cout * Cc * 4, p0 + 2 * cout * Cc * 4 + cout * Cc * 2,
+                                            cout * Cc, stream), "pn_split_bf16")
+                cache = (key, blob)
+                self.__dict__["_mf_split"] = cache
+            p0 = cache[1].data_ptr()
+            bias = conv.bias.data_ptr() if conv.bias is not None else None
             y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device,
                             memory_format=torch.channels_last)
-            nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), wh, wl, conv.bias.data_ptr() if conv.bias is not None else None,
-                                            y.data_ptr(), cout, B * H * W, cout, Cc, stream), "pn_linear_tc_rawa")
+            if bf16x3:   # 3xBF16 (PN_OPT_ENC_BF16X3): same kernel family as the encoder, twice the tensor rate
+                nat.check(lib.pn_linear_tc_bf16x3(x.data_ptr(), p0 + 2 * cout * Cc * 4, p0 + 2 * cout * Cc * 4 + cout * Cc * 2,
+                                                  bias, y.data_ptr(), cout, B * H * W, cout, Cc, stream), "pn_linear_tc_bf16x3")
+            else:
+                nat.check(lib.pn_linear_tc_rawa(x.data_ptr(), p0, p0 + cout * Cc * 4, bias, y.data_ptr(), cout, B * H * W,
+                                                cout, Cc, stream), "pn_linear_tc_rawa")
             return y
         ws = self._scratch("_mf_ws", lib.pn_conv1x1_nhwc_to_nchw_workspace_bytes(cout), x.device)
         y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
