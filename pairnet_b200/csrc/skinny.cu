@@ -201,7 +201,8 @@ int launch_skinny_gemm(const GemmBatch& batch, int maxM, int maxN, int nz, cudaS
   } while (0)
   const long long tiles11 = (long long)cdiv(maxN, 8) * cdiv(maxM, 16) * nz;
   int v = variant;
-  if (v < 10) v = tiles11 > 600 ? 12 : 11;  // measured on B200 (scratch/skinny_ab.py)
+  if (v >= 100) v = tiles11 > 600 ? v - 100 : 11;  // A/B studies: auto rule with another tile for the wide problems
+  else if (v < 10) v = tiles11 > 600 ? 12 : 11;    // measured on B200 (scratch/skinny_ab.py)
   switch (v) {
     case 11: PN_SKINNY(1, 1); break;
     case 12: PN_SKINNY(1, 2); break;
