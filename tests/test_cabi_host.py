@@ -151,6 +151,20 @@ def test_reference_config_loads_unchanged_if_present():
     assert model.bbox_head.num_rel_query == 100 and model.num_classes == 133
 
 
+@pytest.mark.parametrize("name,backbone", [("pairnet_60e.py", "ResNet"), ("pairnet_swinb.py", "SwinTransformer")])
+def test_other_shipped_pairnet_configs_build_unchanged_if_present(name, backbone):
+    """The reference's other CrossHead2 configs (`configs/mask2former/`) load and build unchanged.  `pairnet_balanced.py`
+    only LOADS: it passes `class_weight=` to mmdet's FocalLoss, which that class does not accept either."""
+    path = "/root/reference/configs/mask2former/" + name
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this box")
+    from pairnet_b200.registry import Config, build_detector
+    model = build_detector(Config.fromfile(path).model)
+    assert type(model.bbox_head).__name__ == "CrossHead2" and type(model.backbone).__name__ == backbone
+    bal = Config.fromfile("/root/reference/configs/mask2former/pairnet_balanced.py")   # custom_imports resolve
+    assert bal.model.bbox_head.type == "CrossHead2" and bal.model.bbox_head.rel_cls_loss.type == "FocalLoss"
+
+
 def test_constructor_asserts_mirror_reference():
     from pairnet_b200.registry import build_head
     from tests.util import product_head_cfg
