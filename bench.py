@@ -640,6 +640,24 @@ def config4_e2e_bench(device, flush, stream):
             metas = [dict(batch_input_shape=(1024, 1024), img_shape=(1024, 1024, 3))]
             e0.record(); feats = model.extract_feat(x); e1.record(); model.bbox_head(feats, metas); e2.record()
             torch.cuda.synchronize()
+            # the same step as ONE replayed CUDA graph (Swin-L eager is ~700 launches: launch bound)
+            from pairnet_b200.detector import GraphedForward
+            graphed_ms = None
+            try:
+                runner = GraphedForward(model.forward_dummy, x)
+
+                def gstep():
+                    runner.static_in.copy_(img_host, non_blocking=True)
+                    out = runner()
+                    return out[0]["rel"].to("cpu", non_blocking=True)
+                for _ in range(3):
+                    gstep()
+                torch.cuda.synchronize()
+                graphed_ms = statistics.mean(time_steps(gstep, 10, flush, stream))
+                del runner
+            except Exception as exc:  # capture of the PyTorch plumbing is best effort; the eager figure stands
+                graphed_ms = None
+                graph_error = repr(exc)[:200]
     finally:
         lib.pn_set_option(nat.PN_OPT_SINGLE_PASS, 0)
     n_params = sum(p.numel() for p in model.backbone.parameters())
@@ -649,6 +667,8 @@ def config4_e2e_bench(device, flush, stream):
                     "CrossHead2 at 200/200 queries, 1024x1024, 1 image per GPU, eager launches, H2D + D2H inside the timed region",
             "ms_per_image": ms, "images_per_sec_per_gpu": 1e3 / ms, "backbone_ms": e0.elapsed_time(e1),
             "pixel_decoder_plus_head_ms": e1.elapsed_time(e2), "backbone_params": n_params,
+            "graph_replay": ({"ms_per_image": graphed_ms, "images_per_sec_per_gpu": 1e3 / graphed_ms} if graphed_ms
+                             else {"unavailable": locals().get("graph_error", "?")}),
             "dtype": "bf16-class: backbone bf16 autocast; pixel decoder + head single-pass TF32 on fp32 storage",
             "note": "extrapolated config (the reference ships Swin-B / 100 queries); Swin restated from mmdet 2.25.1, parity unpinned"}
 
