@@ -381,6 +381,30 @@ def test_linear_tc_bf16x3(M, N, K):
     assert rel_err(y, model) < 5e-6
 
 
+def test_linear_tc_bf16x3_rejects_what_it_cannot_run():
+    """No silent fallback: K not a multiple of the 64-channel k-block, an unaligned bias, or the TMA-store epilogue switched
+    off are errors with a message."""
+    from pairnet_b200 import _native as nat
+    lib = nat.load()
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.zeros(256, 96, device="cuda"); wh = torch.zeros(128, 96, dtype=torch.bfloat16, device="cuda")
+    y = torch.zeros(256, 128, device="cuda"); b = torch.zeros(132, device="cuda")
+    assert lib.pn_linear_tc_bf16x3(x.data_ptr(), wh.data_ptr(), wh.data_ptr(), None, y.data_ptr(), 128, 256, 128, 96, st) != 0
+    assert b"K" in lib.pn_last_error_string()
+    x = torch.zeros(256, 128, device="cuda"); wh = torch.zeros(128, 128, dtype=torch.bfloat16, device="cuda")
+    assert lib.pn_linear_tc_bf16x3(x.data_ptr(), wh.data_ptr(), wh.data_ptr(), b.data_ptr() + 4, y.data_ptr(), 128, 256, 128,
+                                   128, st) != 0                                   # bias not 16-byte aligned
+    lib.pn_set_option(nat.PN_OPT_UMMA_TMA_STORE, 0)
+    try:
+        assert lib.pn_linear_tc_bf16x3(x.data_ptr(), wh.data_ptr(), wh.data_ptr(), None, y.data_ptr(), 128, 256, 128, 128,
+                                       st) != 0
+    finally:
+        lib.pn_set_option(nat.PN_OPT_UMMA_TMA_STORE, 1)
+    assert lib.pn_linear_tc_bf16x3(x.data_ptr(), wh.data_ptr(), wh.data_ptr(), None, y.data_ptr(), 128, 256, 128, 128, st) == 0
+    torch.cuda.synchronize()
+    assert float(y.abs().max()) == 0.0
+
+
 def _pixel_decoder(seed=3):
     import os
     from pairnet_b200.registry import Config, PLUGIN_LAYERS
