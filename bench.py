@@ -903,10 +903,13 @@ def run_b200(args, rank, world, local):
                    "image": [IMG_H, IMG_W], "queries": 100, "parallelism": f"dp{world} (replicas, no forward collective)",
                    "l2_flush": "256 MiB read+write between timed steps (outside the event pair)",
                    "cuda_graph": not args.no_graph, "cudnn_benchmark": not args.no_cudnn_benchmark,
-                   "upstream": "ResNet-50 and the pixel decoder's 1x1/3x3 convs on cuDNN (TF32 conv default, as PyTorch); "
-                               "deformable encoder, GroupNorm, FPN merge and mask_feature conv hand-written (3xTF32 / fp32)",
-                   "precision_note": "the fp32 label holds for the hand-written head (3xTF32 / FFMA, fp32-level accuracy); "
-                                     "the upstream cuDNN convolutions run single-pass TF32"},
+                   "upstream": "ResNet-50 and the pixel decoder's 3x3 output conv on cuDNN (TF32 conv default, as PyTorch); the "
+                               "pixel decoder's 1x1 input / lateral convs on the hand-written tcgen05 GEMM (one TF32 pass, following "
+                               "torch.backends.cudnn.allow_tf32 like the cuDNN call they replace); deformable encoder and "
+                               "mask_feature conv on the hand-written 3xBF16 GEMM (fp32 in / out, 3-6e-6 of scale), GroupNorm and "
+                               "FPN merge hand-written fp32",
+                   "precision_note": "the fp32 label holds for the hand-written head (3xTF32 / FFMA, ~1e-6 of scale) and the "
+                                     "encoder (3xBF16, 3-6e-6); the upstream convolutions run single-pass TF32 as in PyTorch"},
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
                 "result": "all_cls_scores (sub,obj,cls,rel,importance) + sub_pos/obj_pos to pinned host; mask tensors stay on device",
