@@ -116,6 +116,8 @@ PN_API int pn_get_option(int key);
                                     run as "3xBF16": raw fp32 activations split into bf16 hi / lo pairs in the SM, weights as
                                     prepared bf16 hi / lo planes, three tcgen05.mma kind::f16 products (twice the TF32 rate),
                                     ~1e-5 of the output scale.  0 = 3xTF32 (~1e-6), as everywhere in the head */
+#define PN_OPT_PPN_EPI2 18       /* default 1: pn_ppn_pair_topk_bf16 on images of one or two tiles (N <= 224) runs TWO epilogue / top-k groups
+                                    of 8 warps, each owning every other image, so the per-image top-k chains of two images overlap; 0 = one */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

@@ -47,7 +47,7 @@ constexpr int TOPK_MAX = 256, CAND_MAX = 1408;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
 constexpr int TAIL_PAD = 2048;      // MMA row over-reads past the last tile (< 16 rows >= N: results never stored) stay inside
 
-struct TopkSmem {
+struct alignas(16) TopkSmem {  // 16-byte aligned: the ranking loop reads the candidates as ulonglong2, and there may be two of these
   unsigned long long cand[CAND_MAX];
   unsigned long long win[TOPK_MAX];
   uint32_t lm[2 * BM];
@@ -71,6 +71,7 @@ struct Params {
   int raw_stages;            // depth of the raw ring
   int acc_stride;            // TMEM columns between the two accumulators
   int tmem_cols;
+  int epi_groups;            // 1, or 2 (bf16, single-tile images): two epilogue groups of 8 warps, one per TMEM accumulator
 };
 
 __device__ __forceinline__ uint32_t order_key(float f) {
@@ -83,7 +84,8 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 __device__ __forceinline__ unsigned long long composite(uint32_t key, uint32_t idx) {
   return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
+// the 8 warps of one epilogue group (named barrier 1 + group)
+__device__ __forceinline__ void epi_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory"); }
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2) {
@@ -193,15 +195,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
   uint8_t* raw_ring = smem;
   uint8_t* lo_ring = smem + (size_t)RS * stage_bytes;
   uint8_t* out_stage = lo_ring + (size_t)(BF16 ? 0 : LO_SLOTS) * stage_bytes + TAIL_PAD;  // [8 warps][32 rows x 128 B], swizzled
-  uint8_t* ctrl = out_stage + NUM_EPI_WARPS * STAGE_TILE;
+  uint8_t* ctrl = out_stage + prm.epi_groups * NUM_EPI_WARPS * STAGE_TILE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);  // [RS<=8] TMA -> splitters
   uint64_t* empty_bar = full_bar + 8;                       // [RS<=8] MMA -> TMA
   uint64_t* split_bar = empty_bar + 8;                      // [2] splitters -> MMA
   uint64_t* lo_empty_bar = split_bar + 2;                   // [2] MMA -> splitters
-  uint64_t* tmem_full_bar = lo_empty_bar + 2;               // [2] MMA -> epilogue
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2] epilogue -> MMA
+  // MMA -> epilogue, [accumulator + 2 * epilogue group]: with two groups a group would otherwise skip the phases of the
+  // other group's tiles, and a parity wait cannot tell phase n from phase n + 2
+  uint64_t* tmem_full_bar = lo_empty_bar + 2;               // [4]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 4;             // [2] epilogue -> MMA
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  TopkSmem& tk = *reinterpret_cast<TopkSmem*>(ctrl + CTRL_BYTES);
+  TopkSmem* tk_base = reinterpret_cast<TopkSmem*>(ctrl + CTRL_BYTES);  // one per epilogue group
 
   const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
       mbar_init(&split_bar[a], NUM_SPLIT_WARPS);
       mbar_init(&lo_empty_bar[a], 1);
       mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_full_bar[a + 2], 1);
       mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -261,8 +266,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
     // ===== MMA issuer (warp-uniform loop, one elected lane issues)
     const uint32_t idesc = BF16 ? make_idesc_bf16(prm.bn) : make_idesc(prm.bn);
     Ring r(RS), l(LO_SLOTS);
-    uint32_t tile_it = 0;
-    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+    uint32_t tile_it = 0, img_it = 0;
+    for (int b = blockIdx.x; b < prm.B; b += gridDim.x, ++img_it) {
+      const uint32_t full_grp = prm.epi_groups == 2 ? 2u * (img_it & 1u) : 0u;  // the epilogue group that owns this image
       for (int t = 0; t < tiles_per_img; ++t, ++tile_it) {
         const uint32_t acc = tile_it & 1;
         mbar_wait(&tmem_empty_bar[acc], ((tile_it >> 1) & 1) ^ 1);
@@ -305,33 +311,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
           }
           __syncwarp();
         }
-        if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+        if (elect_one()) umma_commit(&tmem_full_bar[acc + full_grp]);
         __syncwarp();
       }
     }
-  } else if (warp < 2 + NUM_EPI_WARPS) {
-    // ===== epilogue + top-k: 8 warps.  TMEM lane quadrant = warp % 4 (one matrix row per thread); the two warps of a
+  } else if (warp < 2 + NUM_EPI_WARPS * prm.epi_groups) {
+    // ===== epilogue + top-k: 8 warps per group.  With two groups (bf16 entry point, images of one or two tiles: N <= 224)
+    // group g owns every other image of the CTA: the per-image latency chain of the top-k (~6 us, what bounds the bf16
+    // kernel there) runs for two images at once; the bf16 kernel has no splitter warps, so the CTA still has 18 warps.  TMEM lane quadrant = warp % 4 (one matrix row per thread); the two warps of a
     // quadrant take alternate 32-column chunks (par).  Everything below is latency bound at one warp per scheduler, so
     // the work per element is kept to one or two instructions: float compares against the threshold, keys only for
     // the (rare) candidates.
     const int quad = warp & 3;
-    const int par = (warp - 2) >> 2;
+    const int grp = (warp - 2) / NUM_EPI_WARPS;
+    const int ew = (warp - 2) % NUM_EPI_WARPS;   // warp index inside the group
+    const int par = ew >> 2;
     const int et = par * BM + quad * 32 + lane;  // 0 .. 255
+    TopkSmem& tk = tk_base[grp];
+    const int G = prm.epi_groups;
     const int K = prm.topk;
     uint8_t* sbuf = out_stage + (size_t)(warp - 2) * STAGE_TILE;  // one 32 x 32 fp32 staging tile per epilogue warp
     const float NEG_INF = __uint_as_float(0xff800000u);
     const uint32_t KEY_NEG_INF = order_key(NEG_INF);
     const uint64_t pol_stream = l2_policy_evict_first();
-    uint32_t tile_it = 0;
-    for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
+    uint32_t img_it = (uint32_t)grp;
+    for (int b = blockIdx.x + grp * (int)gridDim.x; b < prm.B; b += G * (int)gridDim.x, img_it += (uint32_t)G) {
       bool have_t0 = false;
       uint32_t t0 = 0;
       float t0f = 0.f;
       if (et == 0) tk.ncand = 0;  // first push happens after the epi_sync that publishes t0
+      uint32_t tile_it = img_it * (uint32_t)tiles_per_img;  // same numbering as the MMA warp (G = 2: one tile per image)
       for (int t = 0; t < tiles_per_img; ++t, ++tile_it) {
         const int m0 = (t / prm.ntiles) * BM, n0 = (t % prm.ntiles) * prm.n_step;
         const uint32_t acc = tile_it & 1;
-        mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
+        // two groups (1 or 2 tiles per image): this group's barrier for `acc` completes once per image of the group
+        if (G == 2) mbar_wait(&tmem_full_bar[acc + 2 * grp], (img_it >> 1) & 1);
+        else mbar_wait(&tmem_full_bar[acc], (tile_it >> 1) & 1);
         tc_fence_after();
         const int row = m0 + quad * 32 + lane;
         const bool rvalid = row < N;
@@ -382,11 +397,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
           // to the 8 warps, each sorts its 32 with shuffles, and every thread ranks its entry by binary search in the
           // other seven sorted lists (an all-pairs count cost 2.5 us per image here, latency bound).
           tk.lm[et] = (order_key(lm) & 0xffffff00u) | (uint32_t)(255 - et);
-          epi_sync();
-          const int ew = warp - 2;
+          epi_sync(grp);
           const uint32_t mine = warp_sort_desc(tk.lm[lane * NUM_EPI_WARPS + ew], lane);
           tk.sl[ew][lane] = mine;
-          epi_sync();
+          epi_sync(grp);
           {
             int rank = lane;  // entries of the own list above this one
 #pragma unroll
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
             }
             if (rank == K - 1) tk.t0 = mine & 0xffffff00u;
           }
-          epi_sync();
+          epi_sync(grp);
           t0 = tk.t0;
           t0f = key_to_float(t0);
           have_t0 = true;
@@ -432,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
           // ---- rank the candidates by counting: win[r] = candidate with r larger candidates (the composite order IS the
           // output order).  Last tile: emit.  Every 4th tile of a multi-tile image: keep the K best so far and raise
           // t0 to the K-th of them, so that the candidate list stays short however many tiles follow.
-          epi_sync();
+          epi_sync(grp);
           const unsigned nc = tk.ncand;
           const bool bad = t0 <= (KEY_NEG_INF | 0xffu) || nc > (unsigned)CAND_MAX || nc < (unsigned)K;
           if (last && et == 0) prm.redo[b] = bad ? 1 : 0;
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
               if (j < nc) r0 += tk.cand[j] > me;
               if (r0 + r1 < (unsigned)K) tk.win[r0 + r1] = me;
             }
-            epi_sync();
+            epi_sync(grp);
             if (last) {
               for (int r = et; r < K; r += 32 * NUM_EPI_WARPS) {
                 const uint32_t idx = 0xffffffffu - (uint32_t)(tk.win[r] & 0xffffffffull);
@@ -465,7 +479,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
               t0f = key_to_float(t0);
             }
           }
-          epi_sync();  // last: smem of this image is recycled by the next one; else: the shortened list is published
+          epi_sync(grp);  // last: smem of this image is recycled by the next one; else: the shortened list is published
         }
       }
     }
@@ -576,7 +590,8 @@ int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, in
   PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box, bf16 ? 64 : BK, bf16));
   PN_TRY(make_map_3d(&prm.c_map, C, B, N, N, 32, 32));
   const int stage = prm.s_tile + prm.o_tile;
-  const int fixed = 1024 + TAIL_PAD + NUM_EPI_WARPS * STAGE_TILE + CTRL_BYTES + (int)sizeof(TopkSmem) + 64;
+  prm.epi_groups = (bf16 && prm.mtiles * prm.ntiles <= 2 && get_option(OPT_PPN_EPI2)) ? 2 : 1;
+  const int fixed = 1024 + TAIL_PAD + prm.epi_groups * (NUM_EPI_WARPS * STAGE_TILE + (int)sizeof(TopkSmem)) + CTRL_BYTES + 64;
   const int lo_slots = bf16 ? 0 : LO_SLOTS;
   int rs = (SMEM_LIMIT - fixed) / stage - lo_slots;
   rs = rs > 8 ? 8 : rs;
@@ -596,7 +611,8 @@ int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, in
   }
   const int num_sms = sm_count();
   const int grid = B < num_sms ? B : num_sms;
-  if (bf16) pair_topk_kernel<true><<<grid, NUM_THREADS - 32 * NUM_SPLIT_WARPS, smem, st>>>(prm);  // no splitter warps
+  if (bf16)  // no splitter warps; one or two epilogue groups
+    pair_topk_kernel<true><<<grid, 64 + 32 * NUM_EPI_WARPS * prm.epi_groups, smem, st>>>(prm);
   else pair_topk_kernel<false><<<grid, NUM_THREADS, smem, st>>>(prm);
   return check_launch("pair_topk_kernel");
 }
