@@ -117,7 +117,9 @@ PN_API int pn_get_option(int key);
                                     prepared bf16 hi / lo planes, three tcgen05.mma kind::f16 products (twice the TF32 rate),
                                     ~1e-5 of the output scale.  0 = 3xTF32 (~1e-6), as everywhere in the head */
 #define PN_OPT_PPN_EPI2 18       /* default 1: pn_ppn_pair_topk_bf16 on images of one or two tiles (N <= 224) runs TWO epilogue / top-k groups
-                                    of 8 warps, each owning every other image, so the per-image top-k chains of two images overlap; 0 = one */
+                                    of 8 warps, each owning every other image, so the per-image top-k chains of two images overlap; 0 = one;
+                                    2 = the fp32 kernel too where shared memory allows (A/B only: measured slower, 0.57 vs 0.62 at N = 100 --
+                                    26 warps and a 2-stage operand ring) */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

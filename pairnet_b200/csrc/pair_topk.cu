@@ -186,7 +186,7 @@ struct Ring {  // (slot, phase) walker over a ring of runtime depth
 // three TF32 passes, a k-block is 64 channels (the same 128-byte swizzle row), and there is nothing to split: the MMA
 // warp takes the raw ring directly and the splitter warps are not launched.  The matrix and the top-k stay fp32 / int64.
 template <bool BF16>
-__global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_constant__ Params prm) {
+__global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk_kernel(const __grid_constant__ Params prm) {
   constexpr int BKE = BF16 ? 64 : BK;  // channels per k-block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) pair_topk_kernel(const __grid_
     tc_fence_before();
   } else if (!BF16) {
     // ===== splitters: lo tiles of S and O (16-byte chunks, swizzled layout preserved); the raw tile is the hi operand
-    const int sid = threadIdx.x - (64 + 32 * NUM_EPI_WARPS);  // 0 .. 255
+    const int sid = threadIdx.x - (64 + 32 * NUM_EPI_WARPS * prm.epi_groups);  // 0 .. 255
     constexpr int NSPLIT = 32 * NUM_SPLIT_WARPS;
     Ring r(RS), l(LO_SLOTS);
     for (int b = blockIdx.x; b < prm.B; b += gridDim.x) {
@@ -590,9 +590,15 @@ int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, in
   PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box, bf16 ? 64 : BK, bf16));
   PN_TRY(make_map_3d(&prm.c_map, C, B, N, N, 32, 32));
   const int stage = prm.s_tile + prm.o_tile;
-  prm.epi_groups = (bf16 && prm.mtiles * prm.ntiles <= 2 && get_option(OPT_PPN_EPI2)) ? 2 : 1;
-  const int fixed = 1024 + TAIL_PAD + prm.epi_groups * (NUM_EPI_WARPS * STAGE_TILE + (int)sizeof(TopkSmem)) + CTRL_BYTES + 64;
+  // PN_OPT_PPN_EPI2: 1 = two groups for the bf16 entry point; 2 = for the fp32 kernel too (A/B studies: 26 warps)
+  prm.epi_groups = (prm.mtiles * prm.ntiles <= 2 && (bf16 ? get_option(OPT_PPN_EPI2) >= 1 : get_option(OPT_PPN_EPI2) >= 2)) ? 2 : 1;
   const int lo_slots = bf16 ? 0 : LO_SLOTS;
+  auto fixed_bytes = [&](int groups) {
+    return 1024 + TAIL_PAD + groups * (NUM_EPI_WARPS * STAGE_TILE + (int)sizeof(TopkSmem)) + CTRL_BYTES + 64;
+  };
+  // the second group's staging tiles and top-k state cost 47 KiB of the operand ring: keep at least 3 raw stages
+  if (prm.epi_groups == 2 && (SMEM_LIMIT - fixed_bytes(2)) / stage - lo_slots < (bf16 ? 3 : 2)) prm.epi_groups = 1;
+  const int fixed = fixed_bytes(prm.epi_groups);
   int rs = (SMEM_LIMIT - fixed) / stage - lo_slots;
   rs = rs > 8 ? 8 : rs;
   PN_REQUIRE(rs >= 2, PN_ERR_UNSUPPORTED, "pair top-k: tiles of N=%d do not fit shared memory", N);
@@ -613,7 +619,7 @@ int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, in
   const int grid = B < num_sms ? B : num_sms;
   if (bf16)  // no splitter warps; one or two epilogue groups
     pair_topk_kernel<true><<<grid, 64 + 32 * NUM_EPI_WARPS * prm.epi_groups, smem, st>>>(prm);
-  else pair_topk_kernel<false><<<grid, NUM_THREADS, smem, st>>>(prm);
+  else pair_topk_kernel<false><<<grid, NUM_THREADS + 32 * NUM_EPI_WARPS * (prm.epi_groups - 1), smem, st>>>(prm);
   return check_launch("pair_topk_kernel");
 }
 
