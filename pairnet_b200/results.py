@@ -50,7 +50,10 @@ def _np(t):
         return t
     t = t.detach()
     if t.is_cuda and t.numel() * t.element_size() >= _PINNED_MIN_BYTES:
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        try:
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        except RuntimeError:      # locked-memory limit of the host: the pageable copy is only slower
+            return t.cpu().numpy()
         host.copy_(t, non_blocking=True)
         torch.cuda.current_stream(t.device).synchronize()
         return host.numpy()
