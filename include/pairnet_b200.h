@@ -120,6 +120,8 @@ PN_API int pn_get_option(int key);
                                     of 8 warps, each owning every other image, so the per-image top-k chains of two images overlap; 0 = one;
                                     2 = the fp32 kernel too where shared memory allows (A/B only: measured slower, 0.57 vs 0.62 at N = 100 --
                                     26 warps and a 2-stage operand ring) */
+#define PN_OPT_PPN_HALF_KB 19    /* default 1: the fp32 pair-matrix + top-k kernel uses 16-channel k-blocks (64-byte rows, SWIZZLE_64B) when
+                                    fewer than four 32-channel raw stages fit shared memory (N >= ~128): twice the ring depth; 0 = always 32 */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

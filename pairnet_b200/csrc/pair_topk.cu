@@ -71,6 +71,7 @@ struct Params {
   int raw_stages;            // depth of the raw ring
   int acc_stride;            // TMEM columns between the two accumulators
   int tmem_cols;
+  int bk;                    // fp32 kernel: channels per k-block, 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B)
   int epi_groups;            // 1, or 2 (bf16, single-tile images): two epilogue groups of 8 warps, one per TMEM accumulator
 };
 
@@ -173,6 +174,17 @@ __device__ __forceinline__ uint32_t warp_sort_desc(uint32_t x, int lane) {
   return x;
 }
 
+// K-major operand tile with 64-byte rows (16 fp32 channels), SWIZZLE_64B: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+
 struct Ring {  // (slot, phase) walker over a ring of runtime depth
   int slot, depth;
   uint32_t phase;
@@ -187,7 +199,11 @@ struct Ring {  // (slot, phase) walker over a ring of runtime depth
 // warp takes the raw ring directly and the splitter warps are not launched.  The matrix and the top-k stay fp32 / int64.
 template <bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk_kernel(const __grid_constant__ Params prm) {
-  constexpr int BKE = BF16 ? 64 : BK;  // channels per k-block
+  // channels per k-block.  fp32: 32, or 16 when the operand tiles are large (N >= ~128): with 32 only two raw stages fit
+  // beside the lo ring and the staging tiles, and two stages do not cover TMA latency + split + MMA (measured 1.35 us per
+  // k-block against 0.9 us of MMAs at N = 200); half-size k-blocks double the ring depth
+  const int BKE = BF16 ? 64 : prm.bk;
+  const bool sw64 = !BF16 && prm.bk == 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int stage_bytes = prm.s_tile + prm.o_tile;
@@ -295,11 +311,14 @@ __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk
           tc_fence_after();
           const uint32_t hi = smem_u32(raw_ring + (size_t)r.slot * stage_bytes);
           const uint32_t lo = smem_u32(lo_ring + (size_t)l.slot * stage_bytes);
-          const uint64_t a_hi = make_smem_desc(hi), b_hi = make_smem_desc(hi + prm.s_tile);
-          const uint64_t a_lo = make_smem_desc(lo), b_lo = make_smem_desc(lo + prm.s_tile);
+          const uint64_t a_hi = sw64 ? make_smem_desc_sw64(hi) : make_smem_desc(hi);
+          const uint64_t b_hi = sw64 ? make_smem_desc_sw64(hi + prm.s_tile) : make_smem_desc(hi + prm.s_tile);
+          const uint64_t a_lo = sw64 ? make_smem_desc_sw64(lo) : make_smem_desc(lo);
+          const uint64_t b_lo = sw64 ? make_smem_desc_sw64(lo + prm.s_tile) : make_smem_desc(lo + prm.s_tile);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k * UMMA_K >= BKE) break;
               const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
               const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
               umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
@@ -496,8 +515,9 @@ __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk
         // Rows past N are zero in the raw tile (TMA fill) or lie past it; whatever the lo tile holds there only
         // reaches output rows / columns >= N, which are never stored nor ranked.
         const int m0 = (t / prm.ntiles) * BM, n0 = (t % prm.ntiles) * prm.n_step;
-        const int chunks_s = ((min(BM, N - m0) + 7) & ~7) * 8;
-        const int chunks_o = ((min(prm.n_step, N - n0) + 7) & ~7) * 8;
+        const int cpr = BKE / 4;  // 16-byte chunks per row of a k-block tile
+        const int chunks_s = ((min(BM, N - m0) + 7) & ~7) * cpr;
+        const int chunks_o = ((min(prm.n_step, N - n0) + 7) & ~7) * cpr;
         const int o_shift = prm.s_tile - chunks_s * 16;  // chunk index -> byte offset jump from the S to the O tile
         for (int kb = 0; kb < num_kb; ++kb, r.next(), l.next()) {
           mbar_wait(&full_bar[r.slot], r.phase);
@@ -532,7 +552,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_map_3d(CUtensorMap* map, const void* ptr, int B, int N, int K, int box_rows, int box_cols = BK,
-                       bool bf16 = false) {
+                       bool bf16 = false, bool swizzle64 = false) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -550,8 +570,8 @@ static int make_map_3d(CUtensorMap* map, const void* ptr, int B, int N, int K, i
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                   const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PN_REQUIRE(r == CUDA_SUCCESS, PN_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
   return 0;
 }
@@ -584,10 +604,16 @@ int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, in
   prm.bn = (int)round_up(prm.n_step, 16);
   const int s_box = (int)round_up(N < BM ? N : BM, 8);
   const int o_box = prm.n_step;
-  prm.s_tile = s_box * BK * 4;
-  prm.o_tile = o_box * BK * 4;
-  PN_TRY(make_map_3d(&prm.s_map, S, B, N, K, s_box, bf16 ? 64 : BK, bf16));
-  PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box, bf16 ? 64 : BK, bf16));
+  // fp32: half-size k-blocks (16 channels, SWIZZLE_64B) when fewer than 4 raw stages of 32 channels would fit
+  prm.bk = BK;
+  if (!bf16 && get_option(OPT_PPN_HALF_KB)) {
+    const int fixed1 = 1024 + TAIL_PAD + NUM_EPI_WARPS * STAGE_TILE + (int)sizeof(TopkSmem) + CTRL_BYTES + 64;
+    if ((SMEM_LIMIT - fixed1) / ((s_box + o_box) * BK * 4) - LO_SLOTS < 4) prm.bk = 16;
+  }
+  prm.s_tile = s_box * prm.bk * 4;
+  prm.o_tile = o_box * prm.bk * 4;
+  PN_TRY(make_map_3d(&prm.s_map, S, B, N, K, s_box, bf16 ? 64 : prm.bk, bf16, prm.bk == 16));
+  PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box, bf16 ? 64 : prm.bk, bf16, prm.bk == 16));
   PN_TRY(make_map_3d(&prm.c_map, C, B, N, N, 32, 32));
   const int stage = prm.s_tile + prm.o_tile;
   // PN_OPT_PPN_EPI2: 1 = two groups for the bf16 entry point; 2 = for the fp32 kernel too (A/B studies: 26 warps)
