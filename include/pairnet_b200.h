@@ -122,6 +122,10 @@ PN_API int pn_get_option(int key);
                                     26 warps and a 2-stage operand ring) */
 #define PN_OPT_PPN_HALF_KB 19    /* default 1: the fp32 pair-matrix + top-k kernel uses 16-channel k-blocks (64-byte rows, SWIZZLE_64B) when
                                     fewer than four 32-channel raw stages fit shared memory (N >= ~128): twice the ring depth; 0 = always 32 */
+#define PN_OPT_PPN_SPECULATE 20  /* default 1: fused pair-matrix + top-k kernel, single-tile images: the ~1.5 K-th largest value of the previous
+                                    image of the CTA is the speculative candidate threshold of the next one (one pass over the accumulator);
+                                    K <= candidates <= 1408 proves the top-K is among them, otherwise the image is redone by the exact
+                                    kernel.  0 = always the exact local-maxima threshold + second pass */
 #define PN_OPT_SKINNY 8         /* default 1: query-side linears (< 1024 rows) on the latency-optimised warp-MMA kernel
                                    (3xTF32, no smem staging, one exposed memory round trip); 0 = k-tiled FFMA kernel */
 /* fills SM count and compute capability of the current device */

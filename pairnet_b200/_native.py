@@ -96,7 +96,7 @@ P = C.POINTER
 # name -> (restype, argtypes); every symbol declared in include/pairnet_b200.h
 PN_OPT_TENSOR_CORES, PN_OPT_OVERLAP, PN_OPT_SKINNY, PN_OPT_MASK_TC, PN_OPT_FUSED_CHAIN = 0, 3, 8, 9, 10  # include/pairnet_b200.h
 PN_OPT_TOPK_RADIX, PN_OPT_PPN_TC, PN_OPT_PPN_FUSED_TOPK, PN_OPT_CONV_TC = 6, 7, 11, 12
-PN_OPT_UMMA_TMA_STORE, PN_OPT_SINGLE_PASS, PN_OPT_NVTX, PN_OPT_PDL, PN_OPT_ENC_BF16X3, PN_OPT_PPN_EPI2, PN_OPT_PPN_HALF_KB = 13, 14, 15, 16, 17, 18, 19
+PN_OPT_UMMA_TMA_STORE, PN_OPT_SINGLE_PASS, PN_OPT_NVTX, PN_OPT_PDL, PN_OPT_ENC_BF16X3, PN_OPT_PPN_EPI2, PN_OPT_PPN_HALF_KB, PN_OPT_PPN_SPECULATE = 13, 14, 15, 16, 17, 18, 19, 20
 
 SIGNATURES = {
     "pn_version": (i32, []),

@@ -23,7 +23,7 @@ static thread_local char g_err[512] = "ok";
 static thread_local int g_launches = 0;
 // Process-wide configuration knobs (pn_set_option): read at launch time by every entry point, meant to be set once
 // before the first forward (tests flip them between calls on one thread); they are not per-call state.
-static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1};
+static int g_options[OPT_COUNT] = {1, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1};
 int get_option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_options[key] : 0; }
 
 NvtxRange::NvtxRange(const char* name) : on(get_option(OPT_NVTX) != 0) { if (on) nvtxRangePushA(name); }

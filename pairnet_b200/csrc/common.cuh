@@ -232,7 +232,7 @@ int launch_level_prep(const float* mem, const float* level_embed, const float* p
 int launch_level_prep_tokens(const float* mem, long long bstride, const float* level_embed, const float* pos, float* x,
                              float* xp, int B, int hw, cudaStream_t st, float* x_lo = nullptr, float* xp_lo = nullptr);
 // runtime options (pn_set_option)
-enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_PPN_FUSED_TOPK = 11, OPT_CONV_TC = 12, OPT_UMMA_TMA_STORE = 13, OPT_SINGLE_PASS = 14, OPT_NVTX = 15, OPT_PDL = 16, OPT_ENC_BF16X3 = 17, OPT_PPN_EPI2 = 18, OPT_PPN_HALF_KB = 19, OPT_COUNT = 20 };
+enum { OPT_TENSOR_CORES = 0, OPT_UMMA_WIDE = 1, OPT_UMMA_EPI8 = 2, OPT_OVERLAP = 3, OPT_FA_TC = 4, OPT_UMMA_RAW_A = 5, OPT_TOPK_RADIX = 6, OPT_PPN_TC = 7, OPT_SKINNY = 8, OPT_MASK_TC = 9, OPT_FUSED_CHAIN = 10, OPT_PPN_FUSED_TOPK = 11, OPT_CONV_TC = 12, OPT_UMMA_TMA_STORE = 13, OPT_SINGLE_PASS = 14, OPT_NVTX = 15, OPT_PDL = 16, OPT_ENC_BF16X3 = 17, OPT_PPN_EPI2 = 18, OPT_PPN_HALF_KB = 19, OPT_PPN_SPECULATE = 20, OPT_COUNT = 21 };
 int get_option(int key);
 int launch_mask_feature_resize(const float* F, float* out, int B, int H, int W, int h, int w, int ldo,
                                cudaStream_t st);

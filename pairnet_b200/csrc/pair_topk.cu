@@ -54,6 +54,7 @@ struct alignas(16) TopkSmem {  // 16-byte aligned: the ranking loop reads the ca
   uint32_t sl[8][32];  // the local maxima as 8 sorted lists
   uint32_t t0;
   unsigned ncand;
+  uint32_t tguess;  // order key of the ~1.5 K-th largest element of the image just ranked: speculative threshold of the next one
 };
 constexpr int CTRL_BYTES = 256;  // mbarriers + TMEM base slot
 constexpr int STAGE_TILE = 32 * 128;  // one 32-row x 32-column fp32 output tile (SWIZZLE_128B)
@@ -72,6 +73,7 @@ struct Params {
   int acc_stride;            // TMEM columns between the two accumulators
   int tmem_cols;
   int bk;                    // fp32 kernel: channels per k-block, 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B)
+  int speculate;             // single-tile images: previous image's ~1.5 K-th value as the first-pass threshold (PN_OPT_PPN_SPECULATE)
   int epi_groups;            // 1, or 2 (bf16, single-tile images): two epilogue groups of 8 warps, one per TMEM accumulator
 };
 
@@ -354,11 +356,21 @@ __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk
     const uint32_t KEY_NEG_INF = order_key(NEG_INF);
     const uint64_t pol_stream = l2_policy_evict_first();
     uint32_t img_it = (uint32_t)grp;
+    // Speculative threshold (single-tile images): the ~1.5 K-th largest value of the PREVIOUS image of this group is used
+    // as the candidate threshold of the next one, in its first and only pass over the accumulator.  If that yields between
+    // K and CAND_MAX candidates they contain the exact top-K (everything left out is smaller than every candidate) and the
+    // local-maxima threshold + second TMEM read (~half of the per-image chain) are skipped; otherwise the image is flagged
+    // and redone by the exact stand-alone kernel, and the next image takes the exact path again.
+    const bool speculate = tiles_per_img == 1 && prm.speculate != 0;
+    bool guess_ok = false;
+    uint32_t guess = 0;
+    if (et == 0) tk.ncand = 0;  // later resets happen at the end of each image, before its last epi_sync
+    epi_sync(grp);
     for (int b = blockIdx.x + grp * (int)gridDim.x; b < prm.B; b += G * (int)gridDim.x, img_it += (uint32_t)G) {
-      bool have_t0 = false;
-      uint32_t t0 = 0;
-      float t0f = 0.f;
-      if (et == 0) tk.ncand = 0;  // first push happens after the epi_sync that publishes t0
+      bool have_t0 = speculate && guess_ok;
+      uint32_t t0 = have_t0 ? guess : 0u;
+      float t0f = have_t0 ? key_to_float(guess) : 0.f;
+      guess_ok = false;
       uint32_t tile_it = img_it * (uint32_t)tiles_per_img;  // same numbering as the MMA warp (G = 2: one tile per image)
       for (int t = 0; t < tiles_per_img; ++t, ++tile_it) {
         const int m0 = (t / prm.ntiles) * BM, n0 = (t % prm.ntiles) * prm.n_step;
@@ -470,6 +482,7 @@ __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk
           const bool bad = t0 <= (KEY_NEG_INF | 0xffu) || nc > (unsigned)CAND_MAX || nc < (unsigned)K;
           if (last && et == 0) prm.redo[b] = bad ? 1 : 0;
           if (!bad) {
+            const unsigned tgt = min(nc, (unsigned)(K + K / 2)) - 1u;  // rank whose key becomes the next image's guess
             for (unsigned i = et; i < nc; i += 32 * NUM_EPI_WARPS) {
               const unsigned long long me = tk.cand[i];
               unsigned r0 = 0, r1 = 0;
@@ -481,8 +494,10 @@ __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk
               }
               if (j < nc) r0 += tk.cand[j] > me;
               if (r0 + r1 < (unsigned)K) tk.win[r0 + r1] = me;
+              if (r0 + r1 == tgt) tk.tguess = (uint32_t)(me >> 32);
             }
             epi_sync(grp);
+            if (last && speculate) { guess = tk.tguess; guess_ok = true; }
             if (last) {
               for (int r = et; r < K; r += 32 * NUM_EPI_WARPS) {
                 const uint32_t idx = 0xffffffffu - (uint32_t)(tk.win[r] & 0xffffffffull);
@@ -498,6 +513,7 @@ __global__ void __launch_bounds__(NUM_THREADS + 32 * NUM_EPI_WARPS, 1) pair_topk
               t0f = key_to_float(t0);
             }
           }
+          if (last && et == 0) tk.ncand = 0;  // the next image may push in its first pass (speculative threshold)
           epi_sync(grp);  // last: smem of this image is recycled by the next one; else: the shortened list is published
         }
       }
@@ -615,6 +631,7 @@ int launch_pair_topk_fused(const void* S, const void* O, bool bf16, float* C, in
   PN_TRY(make_map_3d(&prm.s_map, S, B, N, K, s_box, bf16 ? 64 : prm.bk, bf16, prm.bk == 16));
   PN_TRY(make_map_3d(&prm.o_map, O, B, N, K, o_box, bf16 ? 64 : prm.bk, bf16, prm.bk == 16));
   PN_TRY(make_map_3d(&prm.c_map, C, B, N, N, 32, 32));
+  prm.speculate = get_option(OPT_PPN_SPECULATE) != 0;
   const int stage = prm.s_tile + prm.o_tile;
   // PN_OPT_PPN_EPI2: 1 = two groups for the bf16 entry point; 2 = for the fp32 kernel too (A/B studies: 26 warps)
   prm.epi_groups = (prm.mtiles * prm.ntiles <= 2 && (bf16 ? get_option(OPT_PPN_EPI2) >= 1 : get_option(OPT_PPN_EPI2) >= 2)) ? 2 : 1;

@@ -769,6 +769,38 @@ def test_pair_topk_bf16_rejects_fp32_and_bad_shapes():
         bad.run_embeds_bf16(z, z)
 
 
+@pytest.mark.parametrize("bf16", [False, True])
+def test_pair_topk_speculative_threshold_failures_are_redone_exactly(bf16):
+    """PN_OPT_PPN_SPECULATE: a CTA thresholds image i+1 with the ~1.5 K-th value of image i.  Consecutive images of a CTA
+    (b, b + 148, b + 296 on a 148-SM B200) are given scales 1, 0.01 and 100 here, so the guess leaves no candidate for the
+    second and overflows the candidate buffer for the third: both are flagged and redone by the exact kernel; every
+    image's indices stay exact (ties by ascending flat index)."""
+    import torch.nn.functional as F
+    from oracle.head import stable_topk
+    from pairnet_b200 import _native as nat, ops
+    B, N, K = 3 * 148 + 5, 100, 100
+    g = torch.Generator().manual_seed(9)
+    s = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    o = F.normalize(torch.randn(B, N, 256, generator=g), dim=-1)
+    s[148:296] *= 0.01
+    s[296:444] *= 100.0
+    if bf16:
+        s, o = s.to(torch.bfloat16), o.to(torch.bfloat16)
+    plan = ops.PpnPlan(B, N, K, "cuda")
+    assert nat.load().pn_get_option(nat.PN_OPT_PPN_SPECULATE) == 1
+    run = plan.run_embeds_bf16 if bf16 else plan.run_embeds
+    imp, idx, sp, op = run(s.cuda(), o.cuda())
+    torch.cuda.synchronize()
+    ref = torch.matmul(s.double(), o.double().transpose(1, 2))
+    scale = torch.ones(B, 1, 1, dtype=torch.float64)      # |s_i| |o_j| of each image: the scale 3xTF32 errors are relative to
+    scale[148:296], scale[296:444] = 0.01, 100.0
+    assert float(((imp.cpu().double() - ref).abs() / scale).max()) < 2e-6
+    for b in list(range(0, B, 37)) + [147, 148, 149, 295, 296, 297, 443, 444, B - 1]:
+        want = torch.from_numpy(stable_topk(imp[b].flatten().cpu().numpy(), K))
+        assert torch.equal(idx[b].cpu(), want), b
+        assert torch.equal(sp[b].cpu() * N + op[b].cpu(), want), b
+
+
 def test_ppn_l2_chunked_batch_equals_unchunked():
     """Batches whose pair matrices exceed the L2 chunk budget are walked chunk by chunk: same results."""
     import torch.nn.functional as F
